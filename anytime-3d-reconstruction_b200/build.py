@@ -1,0 +1,72 @@
+"""In-tree build of liba3d.so (sm_100a only).  nvcc cross-compiles without a GPU.
+
+    python -m importlib ... or:  python anytime-3d-reconstruction_b200/build.py [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, 'csrc', '_obj')
+LIB = os.path.join(HERE, 'liba3d.so')
+SOURCES = ['handle.cu', 'convt_tc.cu', 'simt_layers.cu', 'tail.cu', 'aux_kernels.cu']
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
+         '--expt-relaxed-constexpr']
+
+
+def _nvcc() -> str:
+    nv = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nv):
+        raise RuntimeError('nvcc not found; liba3d cannot be built')
+    return nv
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    nv = _nvcc()
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    headers.append(os.path.join(HERE, '..', 'include', 'a3d.h'))
+    jobs = []
+    objs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace('.cu', '.o'))
+        objs.append(o)
+        if force or not _newer(o, [s] + headers):
+            cmd = [nv] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd, r
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        for cmd, r in ex.map(run, jobs):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError('nvcc failed for ' + cmd[-3])
+    if force or jobs or not os.path.exists(LIB):
+        cmd = [nv] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('link failed')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

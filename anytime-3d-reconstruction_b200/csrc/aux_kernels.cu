@@ -1,0 +1,184 @@
+// Memory-bound helper kernels of the anytime path:
+//   impute   -- sampling() + mask / fill logic, function.py:35-38, nolbo.py:1472-1486,1505-1510,431-439
+//   counts   -- voxelPrecisionRecall(), function.py:100-115 (stand-alone form on fp32 grids)
+//   pack     -- fp32 {0,1} targets (loader layout, pascal3D.py:149-152) -> 1 bit / voxel
+#include "internal.h"
+
+namespace a3d {
+namespace {
+
+// Philox4x32-10 (Salmon et al. 2011).  Counter (c0..c3), key (k0, k1).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, float& n1) {
+  const float u0 = fmaf((float)w0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (w + 0.5) * 2^-32
+  const float u1 = fmaf((float)w1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-2.f * logf(u0));
+  float s, c;
+  sincospif(2.f * u1, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// One block per object.  z, mask: [B, D]; mu: [C, D]; z_out: [B, K, D].
+__global__ void __launch_bounds__(128)
+impute_kernel(const float* __restrict__ z, const float* __restrict__ mask, const float* __restrict__ mu, int C, int K,
+              int D, uint64_t seed, uint64_t obj_offset, int fill, float* __restrict__ z_out,
+              int32_t* __restrict__ cstar_out) {
+  extern __shared__ float sm[];
+  float* zf = sm;            // [D] filled latent
+  float* mk = zf + D;        // [D] mask
+  float* dist = mk + D;      // [C]
+  __shared__ int cstar_s;
+  const int64_t b = blockIdx.x;
+  const uint64_t obj = obj_offset + (uint64_t)b;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float m = mask[b * D + d];
+    float v = z[b * D + d] * m;                       // nolbo.py:1477
+    if (fill != A3D_FILL_NORMAL && v == 0.f) {        // nolbo.py:1481-1482: where(z == 0) <- mean_c(mu)
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += mu[(size_t)c * D + d];
+      v = s / (float)C;
+    }
+    zf[d] = v;
+    mk[d] = m;
+  }
+  __syncthreads();
+  if (fill != A3D_FILL_NORMAL) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // nolbo.py:1505: sum_d mask * (z - mu_c)^2
+      float s = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float t = zf[d] - mu[(size_t)c * D + d];
+        s = fmaf(mk[d] * t, t, s);
+      }
+      dist[c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = 0;
+      for (int c = 1; c < C; ++c)
+        if (dist[c] < dist[best]) best = c;             // tf.argmin: first minimum
+      cstar_s = best;
+      if (cstar_out) cstar_out[b] = best;
+    }
+    __syncthreads();
+  } else if (threadIdx.x == 0 && cstar_out) {
+    cstar_out[b] = -1;
+  }
+  const int nq = (D + 3) >> 2;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = threadIdx.x; i < K * nq; i += blockDim.x) {
+    const int k = i / nq, q = i % nq;
+    float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (fill != A3D_FILL_MEAN) {
+      const uint4 w = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)k, (uint32_t)obj, (uint32_t)(obj >> 32)), key);
+      box_muller(w.x, w.y, nrm[0], nrm[1]);
+      box_muller(w.z, w.w, nrm[2], nrm[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = q * 4 + e;
+      if (d >= D) break;
+      float v = zf[d];
+      if (fill == A3D_FILL_PRIOR_SAMPLE) {
+        if (mk[d] == 0.f) v = mu[(size_t)cstar_s * D + d] + nrm[e];   // nolbo.py:1508-1510, sigma = 1
+      } else if (fill == A3D_FILL_NORMAL) {
+        if (v == 0.f) v = nrm[e];                                      // nolbo.py:437-439
+      }
+      z_out[((size_t)b * K + k) * D + d] = v;
+    }
+  }
+}
+
+// counts[b] += {TP, FP, FN};  grid = (chunks, B).  V % 4 == 0.
+__global__ void __launch_bounds__(256)
+counts_kernel(const float* __restrict__ target, const float* __restrict__ pred, int64_t V, float thr,
+              unsigned long long* __restrict__ counts) {
+  const int64_t b = blockIdx.y;
+  const float4* t4 = reinterpret_cast<const float4*>(target + b * V);
+  const float4* p4 = reinterpret_cast<const float4*>(pred + b * V);
+  int tp = 0, fp = 0, fn = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < V / 4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 t = __ldg(t4 + i), p = __ldg(p4 + i);
+    const float tv[4] = {t.x, t.y, t.z, t.w}, pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int y = pv[e] >= thr, g = tv[e] > 0.5f;
+      tp += g & y;
+      fp += (1 - g) & y;
+      fn += g & (1 - y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tp += __shfl_xor_sync(0xffffffffu, tp, o);
+    fp += __shfl_xor_sync(0xffffffffu, fp, o);
+    fn += __shfl_xor_sync(0xffffffffu, fn, o);
+  }
+  __shared__ int red[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = tp; red[1][warp] = fp; red[2][warp] = fn; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s) atomicAdd(counts + b * 3 + threadIdx.x, (unsigned long long)s);
+  }
+}
+
+// bits[i] packs voxels 8i..8i+7 (bit e = voxel 8i + e).  total = B*V/8 bytes.
+__global__ void pack_kernel(const float* __restrict__ target, int64_t total_bytes, uint8_t* __restrict__ bits) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_bytes;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(target) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(target) + 2 * i + 1);
+    uint32_t v = (a.x > 0.5f) | ((a.y > 0.5f) << 1) | ((a.z > 0.5f) << 2) | ((a.w > 0.5f) << 3) | ((b.x > 0.5f) << 4) |
+                 ((b.y > 0.5f) << 5) | ((b.z > 0.5f) << 6) | ((b.w > 0.5f) << 7);
+    bits[i] = (uint8_t)v;
+  }
+}
+
+}  // namespace
+
+int launch_impute(const float* z, const float* mask, const float* mu, int C, int64_t B, int K, int D, uint64_t seed,
+                  uint64_t obj_offset, int fill, float* z_out, int32_t* cstar, cudaStream_t st, int64_t* launches) {
+  if (B <= 0) return A3D_OK;
+  const size_t smem = (size_t)(2 * D + (C > 0 ? C : 1)) * sizeof(float);
+  impute_kernel<<<(unsigned)B, 128, smem, st>>>(z, mask, mu, C, K, D, seed, obj_offset, fill, z_out, cstar);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, float thr, unsigned long long* counts,
+                  cudaStream_t st, int64_t* launches) {
+  if (B <= 0) return A3D_OK;
+  int chunks = (int)((V / 4 + 256 * 8 - 1) / (256 * 8));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, (unsigned)B);
+  counts_kernel<<<grid, 256, 0, st>>>(target, pred, V, thr, counts);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+int launch_pack(const float* target, int64_t B, int64_t V, uint8_t* bits, cudaStream_t st, int64_t* launches) {
+  const int64_t total = B * V / 8;
+  if (total <= 0) return A3D_OK;
+  const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  pack_kernel<<<grid, 256, 0, st>>>(target, total, bits);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+}  // namespace a3d

@@ -1,0 +1,333 @@
+// Stride-2 transposed 3-D convolution (k = 4, padding 'same') + folded BatchNorm + activation as a tcgen05
+// implicit GEMM for sm_100a.  Replaces conv3DDec(), /root/reference/src/net_core/autoencoder3D.py:41-54, for the
+// three stride-2 hidden layers (512->256, 256->128, 128->64).
+//
+// Formulation.  Output voxel o = 2j + p (p = parity per axis) receives input voxels j + delta with tap
+// t = p + 1 - 2*delta:   p = 0: delta in {-1, 0} (taps 3, 1);   p = 1: delta in {0, +1} (taps 2, 0).
+// Each output-parity class is therefore a 2x2x2 gather conv over the input grid:
+//     D[(n, j), co] = sum_{delta, ci} X[n, j + delta, ci] * W[t(p, delta), co, ci]        (zero outside the grid)
+//
+// Tiling.  One work unit = one input row (fixed d, h; all W positions along w) x NT = 128 / W decodes = 128 GEMM rows,
+// for a fixed (pd, ph) and BOTH pw parities (COUT <= 128) or one pw (COUT = 256).  GEMM rows are ordered
+// (w major, decode minor), so a shift of the input by delta_w = +-1 is a shift by NT rows = a multiple of the
+// 1024-byte swizzle atom: ONE TMA box (64 ch, NT decodes, W + 2 positions incl. zero-filled halo) serves all three
+// delta_w via the start address of the UMMA shared-memory descriptor.  The out-of-bounds fill of TMA is the
+// 'same' padding.  delta_w = 0 feeds both pw parities in a single MMA of N = 2*COUT.
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue
+// (tcgen05.ld -> scale/shift -> activation -> 16-bit -> global).  Accumulators are double-buffered in TMEM so the
+// epilogue of unit i overlaps the main loop of unit i + 1.  Persistent CTAs, static round-robin unit schedule.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace a3d {
+
+namespace {
+
+template <int CIN_, int COUT_, int WIN_>
+struct Cfg {
+  static constexpr int CIN = CIN_, COUT = COUT_, WIN = WIN_;
+  static constexpr int NT = 128 / WIN;                    // decodes per unit
+  static constexpr bool PWB = (COUT <= 128);              // both pw parities in one unit
+  static constexpr int NPAR = PWB ? 4 : 8;                // parity classes per position
+  static constexpr int NACC = PWB ? 2 * COUT : COUT;      // fp32 accumulator columns per unit
+  static constexpr int TMEM_COLS = (2 * NACC <= 256) ? 256 : 512;
+  static constexpr int CHUNKS = CIN / 64;                 // 64-channel K chunks
+  static constexpr int A_BYTES = (WIN + 2) * NT * 128;    // one input row incl. halo, one chunk
+  static constexpr int BROWS = PWB ? 4 * COUT : 2 * COUT; // weight rows per (sd, sh, chunk)
+  static constexpr int BSLOT_ROWS = 256;
+  static constexpr int BSLOTS = BROWS / BSLOT_ROWS;       // weight slots per input row
+  static constexpr int B_BYTES = BSLOT_ROWS * 128;
+  static constexpr int A_STAGES = 3;
+  static constexpr int B_STAGES = 4;
+  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + NUM_BARS * 8 +
+                                    16 + 2 * NACC * 4;
+  static_assert(BROWS % BSLOT_ROWS == 0, "weight rows per input row must fill whole slots");
+  static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
+};
+
+__device__ __forceinline__ float activate(float v, int act) {
+  if (act == A3D_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  if (act == A3D_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == A3D_ACT_LRELU) return v > 0.f ? v : 0.3f * v;
+  return v;
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (FMT == A3D_DTYPE_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+template <class C, int FMT>
+__global__ void __launch_bounds__(256, 1)
+convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
+                   uint16_t* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
+                   int n_blocks, int n_alloc, int act) {
+  constexpr int CIN = C::CIN, COUT = C::COUT, WIN = C::WIN, NT = C::NT, NACC = C::NACC;
+  (void)CIN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::A_STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::B_STAGES * C::B_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + C::A_STAGES;
+  uint64_t* b_full = a_empty + C::A_STAGES;
+  uint64_t* b_empty = b_full + C::B_STAGES;
+  uint64_t* t_full = b_empty + C::B_STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_shift = s_scale + NACC;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = n_blocks * WIN * WIN * C::NPAR;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_act);
+    ptx::prefetch_tmap(&tmap_wgt);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::B_STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish<1>();
+  }
+  for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+    s_scale[i] = scale[i % COUT];
+    s_shift[i] = shift[i % COUT];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int par = u % C::NPAR;
+        const int pos = u / C::NPAR;
+        const int h = pos % WIN, d = (pos / WIN) % WIN, nb = pos / (WIN * WIN);
+        const int pd = C::PWB ? (par >> 1) : (par >> 2);
+        const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
+        for (int sd = 0; sd < 2; ++sd) {
+          const int id = d + sd - 1 + pd;
+          if (id < 0 || id >= WIN) continue;
+          for (int sh = 0; sh < 2; ++sh) {
+            const int ih = h + sh - 1 + ph;
+            if (ih < 0 || ih >= WIN) continue;
+            for (int c = 0; c < C::CHUNKS; ++c) {
+              const int as = a_it % C::A_STAGES;
+              ptx::mbar_wait(&a_empty[as], ((a_it / C::A_STAGES) & 1) ^ 1);
+              ptx::mbar_expect_tx(&a_full[as], C::A_BYTES);
+              ptx::tma_load_5d(smem_a + as * C::A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, ih, id);
+              ++a_it;
+              const int row0 = ((((par * 2 + sd) * 2 + sh) * C::CHUNKS) + c) * C::BROWS;
+#pragma unroll
+              for (int j = 0; j < C::BSLOTS; ++j) {
+                const int bs = b_it % C::B_STAGES;
+                ptx::mbar_wait(&b_empty[bs], ((b_it / C::B_STAGES) & 1) ^ 1);
+                ptx::mbar_expect_tx(&b_full[bs], C::B_BYTES);
+                ptx::tma_load_2d(smem_b + bs * C::B_BYTES, &tmap_wgt, &b_full[bs], 0, row0 + j * C::BSLOT_ROWS);
+                ++b_it;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0, unit_it = 0;
+      constexpr uint32_t idesc_full = ptx::make_idesc_f16(128, NACC > 256 ? 256 : NACC, FMT);
+      constexpr uint32_t idesc_half = ptx::make_idesc_f16(128, COUT, FMT);
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+        const int par = u % C::NPAR;
+        const int pos = u / C::NPAR;
+        const int h = pos % WIN, d = (pos / WIN) % WIN;
+        const int pd = C::PWB ? (par >> 1) : (par >> 2);
+        const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
+        const int pw = par & 1;  // only meaningful when !PWB
+        const int buf = unit_it & 1;
+        ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * NACC;
+        uint32_t accum = 0;
+        for (int sd = 0; sd < 2; ++sd) {
+          const int id = d + sd - 1 + pd;
+          if (id < 0 || id >= WIN) continue;
+          for (int sh = 0; sh < 2; ++sh) {
+            const int ih = h + sh - 1 + ph;
+            if (ih < 0 || ih >= WIN) continue;
+            for (int c = 0; c < C::CHUNKS; ++c) {
+              const int as = a_it % C::A_STAGES;
+              ptx::mbar_wait(&a_full[as], (a_it / C::A_STAGES) & 1);
+              const uint32_t a_addr = ptx::smem_u32(smem_a + as * C::A_BYTES);
+#pragma unroll
+              for (int j = 0; j < C::BSLOTS; ++j) {
+                const int bs = b_it % C::B_STAGES;
+                ptx::mbar_wait(&b_full[bs], (b_it / C::B_STAGES) & 1);
+                ptx::tc_fence_after();
+                const uint32_t b_addr = ptx::smem_u32(smem_b + bs * C::B_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint32_t ko = kk * 32;  // 16 elements * 2 bytes inside the 128-byte swizzled row
+                  if constexpr (C::PWB && C::BSLOTS == 1) {
+                    // COUT = 64: [0,128) = (pw0,tw1 | pw1,tw2) dw=0; [128,192) = pw0,tw3 dw=-1; [192,256) = pw1,tw0 dw=+1
+                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + NT * 128 + ko, 1024),
+                                     ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                    accum = 1;
+                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + ko, 1024),
+                                     ptx::make_sw128_kmajor_desc(b_addr + 2 * COUT * 128 + ko, 1024), idesc_half, 1);
+                    ptx::umma_f16<1>(tacc + COUT, ptx::make_sw128_kmajor_desc(a_addr + 2 * NT * 128 + ko, 1024),
+                                     ptx::make_sw128_kmajor_desc(b_addr + 3 * COUT * 128 + ko, 1024), idesc_half, 1);
+                  } else if constexpr (C::PWB) {
+                    // COUT = 128: slot 0 = (pw0,tw1 | pw1,tw2) dw=0 (N = 256); slot 1 = pw0,tw3 dw=-1 | pw1,tw0 dw=+1
+                    if (j == 0) {
+                      ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + NT * 128 + ko, 1024),
+                                       ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                      accum = 1;
+                    } else {
+                      ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + ko, 1024),
+                                       ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_half, 1);
+                      ptx::umma_f16<1>(tacc + COUT, ptx::make_sw128_kmajor_desc(a_addr + 2 * NT * 128 + ko, 1024),
+                                       ptx::make_sw128_kmajor_desc(b_addr + COUT * 128 + ko, 1024), idesc_half, 1);
+                    }
+                  } else {
+                    // COUT = 256, one pw per unit: slot 0 = dw=0 tap, slot 1 = dw=+-1 tap
+                    const uint32_t a_off = (j == 0) ? NT * 128 : (pw ? 2 * NT * 128 : 0);
+                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + a_off + ko, 1024),
+                                     ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                    accum = 1;
+                  }
+                }
+                ptx::umma_commit<1>(&b_empty[bs]);  // slot reusable once these MMAs retire
+                ++b_it;
+              }
+              ptx::umma_commit<1>(&a_empty[as]);
+              ++a_it;
+            }
+          }
+        }
+        ptx::umma_commit<1>(&t_full[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: TMEM -> BN/act -> 16-bit -> global
+    const int row = threadIdx.x - 128;                 // TMEM lane == GEMM row
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int w = row / NT;
+    const int nloc = row % NT;
+    constexpr int OD = 2 * WIN;
+    uint32_t unit_it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+      const int par = u % C::NPAR;
+      const int pos = u / C::NPAR;
+      const int h = pos % WIN, d = (pos / WIN) % WIN, nb = pos / (WIN * WIN);
+      const int pd = C::PWB ? (par >> 1) : (par >> 2);
+      const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
+      const int buf = unit_it & 1;
+      const int n = nb * NT + nloc;
+      ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + lane_base + buf * NACC;
+#pragma unroll 1
+      for (int g = 0; g < NACC / 32; ++g) {
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld16(tacc + g * 32, v0);
+        ptx::tmem_ld16(tacc + g * 32 + 16, v1);
+        ptx::tmem_ld_wait();
+        const int col = g * 32;
+        const int pw = C::PWB ? (col / COUT) : (par & 1);
+        const int co = col % COUT;
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x0 = __uint_as_float(v0[2 * i]) * s_scale[col + 2 * i] + s_shift[col + 2 * i];
+          float x1 = __uint_as_float(v0[2 * i + 1]) * s_scale[col + 2 * i + 1] + s_shift[col + 2 * i + 1];
+          o[i] = pack2<FMT>(activate(x0, act), activate(x1, act));
+          float y0 = __uint_as_float(v1[2 * i]) * s_scale[col + 16 + 2 * i] + s_shift[col + 16 + 2 * i];
+          float y1 = __uint_as_float(v1[2 * i + 1]) * s_scale[col + 16 + 2 * i + 1] + s_shift[col + 16 + 2 * i + 1];
+          o[8 + i] = pack2<FMT>(activate(y0, act), activate(y1, act));
+        }
+        if (n < n_alloc) {
+          const size_t vox = (((size_t)n * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * w + pw);
+          uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + co);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+          dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&t_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+}
+
+template <class C>
+int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
+               cudaStream_t st) {
+  const int n_blocks = (int)((n + C::NT - 1) / C::NT);
+  const int total_units = n_blocks * C::WIN * C::WIN * C::NPAR;
+  int grid = num_sms < total_units ? num_sms : total_units;
+  // keep the parity class of a CTA fixed across its units (weights of one class stay hot in L2 / same rows)
+  if (grid > C::NPAR) grid -= grid % C::NPAR;
+  auto launch = [&](auto kern) -> int {
+    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    kern<<<grid, 256, C::SMEM_BYTES, st>>>(L.tmap_act, L.tmap_wgt, reinterpret_cast<uint16_t*>(out), L.scale, L.shift,
+                                           n_blocks, (int)n_alloc, act);
+    A3D_CUDA_OK(cudaGetLastError());
+    return A3D_OK;
+  };
+  if (fmt == A3D_DTYPE_F16) return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16>);
+  return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16>);
+}
+
+}  // namespace
+
+size_t convt_tc_smem_bytes(int cin, int cout, int win) {
+  if (cin == 512 && cout == 256 && win == 4) return Cfg<512, 256, 4>::SMEM_BYTES;
+  if (cin == 256 && cout == 128 && win == 8) return Cfg<256, 128, 8>::SMEM_BYTES;
+  if (cin == 128 && cout == 64 && win == 16) return Cfg<128, 64, 16>::SMEM_BYTES;
+  return 0;
+}
+
+int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
+                       cudaStream_t st, int64_t* launches) {
+  int rc;
+  if (L.cin == 512 && L.cout == 256 && L.win == 4)
+    rc = launch_cfg<Cfg<512, 256, 4>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  else if (L.cin == 256 && L.cout == 128 && L.win == 8)
+    rc = launch_cfg<Cfg<256, 128, 8>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  else if (L.cin == 128 && L.cout == 64 && L.win == 16)
+    rc = launch_cfg<Cfg<128, 64, 16>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  else {
+    set_error("tcgen05 ConvT path supports (512->256,W4), (256->128,W8), (128->64,W16); got %d->%d W%d", L.cin,
+              L.cout, L.win);
+    return A3D_ERR_INVALID;
+  }
+  if (rc == A3D_OK && launches) ++*launches;
+  return rc;
+}
+
+}  // namespace a3d

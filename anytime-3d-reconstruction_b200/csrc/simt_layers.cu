@@ -1,0 +1,175 @@
+// CUDA-core kernels: Dense + BN + act (linearTransform, autoencoder3D.py:56-70), the stride-1 ConvT layer
+// (conv3DDec with strides=1, autoencoder3D.py:41-54,127-128; 0.2 % of the decoder FLOPs) and a direct stride-2
+// ConvT used only as an on-device diagnostic for the tcgen05 kernel (A3D_IMPL_SIMT).
+#include "cvt.cuh"
+#include "internal.h"
+
+namespace a3d {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense(D -> 512) + bias + folded BN + activation.  One block per decode, one thread per output unit.
+// out a0[n][512] is the NDHWC tensor [n,4,4,4,8] (tf.reshape at autoencoder3D.py:125 keeps the flat order).
+template <int FMT>
+__global__ void dense_kernel(const float* __restrict__ z, int D, const float* __restrict__ wd,
+                             const float* __restrict__ bias, const float* __restrict__ scale,
+                             const float* __restrict__ shift, uint16_t* __restrict__ a0, int units, int act) {
+  extern __shared__ float zs[];
+  const int64_t n = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) zs[i] = z[n * D + i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < units; j += blockDim.x) {
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc = fmaf(zs[d], wd[(size_t)d * units + j], acc);
+    acc += bias[j];
+    a0[n * units + j] = from_f32<FMT>(apply_act(acc * scale[j] + shift[j], act));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ConvT3D k=4 s=1 'same' (pad 1 before / 2 after): out[o, co] = sum_{t, ci} in[o - t + 1, ci] * W[t, co, ci].
+// 4^3 x 8 -> 4^3 x 512.  Block = NB decodes x 512 output channels; weights [tap][ci][co] read once per NB decodes.
+template <int FMT, int NB>
+__global__ void __launch_bounds__(512)
+convt_s1_kernel(const uint16_t* __restrict__ a0, const uint16_t* __restrict__ w_tco, const float* __restrict__ scale,
+                const float* __restrict__ shift, uint16_t* __restrict__ a1, int64_t n_total, int cin, int cout,
+                int act) {
+  extern __shared__ float xs[];  // [NB][64 pos][cin]
+  const int64_t n0 = (int64_t)blockIdx.x * NB;
+  const int per = 64 * cin;
+  for (int i = threadIdx.x; i < NB * per; i += blockDim.x) {
+    const int64_t n = n0 + i / per;
+    xs[i] = n < n_total ? to_f32<FMT>(a0[n * per + i % per]) : 0.f;
+  }
+  __syncthreads();
+  const int co = threadIdx.x;
+  if (co >= cout) return;
+  const float sc = scale[co], sh = shift[co];
+  for (int o = 0; o < 64; ++o) {
+    const int od = o >> 4, oh = (o >> 2) & 3, ow = o & 3;
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int td = 0; td < 4; ++td) {
+      const int id = od - td + 1;
+      if (id < 0 || id > 3) continue;
+      for (int th = 0; th < 4; ++th) {
+        const int ih = oh - th + 1;
+        if (ih < 0 || ih > 3) continue;
+        for (int tw = 0; tw < 4; ++tw) {
+          const int iw = ow - tw + 1;
+          if (iw < 0 || iw > 3) continue;
+          const int tap = (td * 4 + th) * 4 + tw;
+          const int ipos = (id * 4 + ih) * 4 + iw;
+          for (int ci = 0; ci < cin; ++ci) {
+            const float wv = to_f32<FMT>(w_tco[((size_t)tap * cin + ci) * cout + co]);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = fmaf(xs[b * per + ipos * cin + ci], wv, acc[b]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int64_t n = n0 + b;
+      if (n < n_total) a1[(n * 64 + o) * cout + co] = from_f32<FMT>(apply_act(acc[b] * sc + sh, act));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Direct stride-2 ConvT (diagnostic).  One block per (decode, output voxel group); thread = output channel.
+template <int FMT>
+__global__ void convt_s2_simt_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ w_tco,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     uint16_t* __restrict__ out, int win, int cin, int cout, int act,
+                                     int64_t total_vox) {
+  extern __shared__ float xs[];  // [8 taps][cin]
+  const int od_ = 2 * win;
+  for (int64_t v = blockIdx.x; v < total_vox; v += gridDim.x) {
+    const int ow = v % od_, oh = (v / od_) % od_, od = (v / ((int64_t)od_ * od_)) % od_;
+    const int64_t n = v / ((int64_t)od_ * od_ * od_);
+    int taps[8];
+    __syncthreads();
+    for (int s = 0; s < 8; ++s) {
+      const int sd = s >> 2, sh = (s >> 1) & 1, sw = s & 1;
+      const int pd = od & 1, ph = oh & 1, pw = ow & 1;
+      const int id = (od >> 1) + sd - 1 + pd, ih = (oh >> 1) + sh - 1 + ph, iw = (ow >> 1) + sw - 1 + pw;
+      // tap = p + 1 - 2*delta, delta = s - 1 + p
+      const int td = pd + 1 - 2 * (sd - 1 + pd), th = ph + 1 - 2 * (sh - 1 + ph), tw = pw + 1 - 2 * (sw - 1 + pw);
+      const bool ok = id >= 0 && id < win && ih >= 0 && ih < win && iw >= 0 && iw < win;
+      taps[s] = ok ? (td * 4 + th) * 4 + tw : -1;
+      for (int c = threadIdx.x; c < cin; c += blockDim.x)
+        xs[s * cin + c] = ok ? to_f32<FMT>(in[((((size_t)n * win + id) * win + ih) * win + iw) * cin + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < 8; ++s) {
+        if (taps[s] < 0) continue;
+        const uint16_t* wp = w_tco + (size_t)taps[s] * cin * cout + co;
+        for (int c = 0; c < cin; ++c) acc = fmaf(xs[s * cin + c], to_f32<FMT>(wp[(size_t)c * cout]), acc);
+      }
+      out[(size_t)v * cout + co] = from_f32<FMT>(apply_act(acc * scale[co] + shift[co], act));
+    }
+  }
+}
+
+template <int FMT>
+__global__ void to_f32_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = to_f32<FMT>(src[i]);
+}
+
+}  // namespace
+
+int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const float* bd, const float* s0,
+                    const float* h0, void* a0, const void* w1_tco, const float* s1, const float* h1, void* a1,
+                    int fmt, int act, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return A3D_OK;
+  constexpr int NB = 8;
+  const int blocks1 = (int)((n + NB - 1) / NB);
+  const size_t smem1 = (size_t)NB * 64 * 8 * sizeof(float);
+  if (fmt == A3D_DTYPE_F16) {
+    dense_kernel<A3D_DTYPE_F16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
+    convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 512, smem1, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+                                                                   (uint16_t*)a1, n, 8, 512, act);
+  } else {
+    dense_kernel<A3D_DTYPE_BF16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
+    convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 512, smem1, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+                                                                    (uint16_t*)a1, n, 8, 512, act);
+  }
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) *launches += 2;
+  return A3D_OK;
+}
+
+int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t n, int fmt, int act, cudaStream_t st,
+                         int64_t* launches) {
+  const int od = 2 * L.win;
+  const int64_t total = n * od * od * od;
+  const int grid = (int)(total < 148 * 16 ? total : 148 * 16);
+  const int threads = L.cout < 256 ? (L.cout < 64 ? 64 : L.cout) : 256;
+  const size_t smem = (size_t)8 * L.cin * sizeof(float);
+  if (fmt == A3D_DTYPE_F16)
+    convt_s2_simt_kernel<A3D_DTYPE_F16><<<grid, threads, smem, st>>>((const uint16_t*)in, (const uint16_t*)L.wgt_tco, L.scale,
+                                                                    L.shift, (uint16_t*)out, L.win, L.cin, L.cout, act, total);
+  else
+    convt_s2_simt_kernel<A3D_DTYPE_BF16><<<grid, threads, smem, st>>>((const uint16_t*)in, (const uint16_t*)L.wgt_tco, L.scale,
+                                                                     L.shift, (uint16_t*)out, L.win, L.cin, L.cout, act, total);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+int launch_to_f32(const void* src, float* dst, int64_t n, int fmt, cudaStream_t st) {
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  if (fmt == A3D_DTYPE_F16)
+    to_f32_kernel<A3D_DTYPE_F16><<<grid, 256, 0, st>>>((const uint16_t*)src, dst, n);
+  else
+    to_f32_kernel<A3D_DTYPE_BF16><<<grid, 256, 0, st>>>((const uint16_t*)src, dst, n);
+  A3D_CUDA_OK(cudaGetLastError());
+  return A3D_OK;
+}
+
+}  // namespace a3d

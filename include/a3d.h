@@ -1,0 +1,132 @@
+/*
+ * a3d.h -- C ABI of the B200-native anytime voxel-decoder hot path.
+ *
+ * The reference (bogus2000/anytime-3D-reconstruction) is 100 % Python/TensorFlow: the path sits behind Python
+ * callables, not an FFI.  Each entry point below names the reference interface it replaces (paths relative to
+ * /root/reference).  All functions return 0 on success or a negative a3d_status; the message of the last error on
+ * the calling thread is available from a3d_last_error().  CUDA errors are sticky on the handle.
+ *
+ * Ownership: the caller owns every input/output buffer; the library owns weights, tensor maps and one workspace
+ * arena sized at create time.  No allocation happens inside the hot calls.  A handle is NOT thread-safe: use one
+ * handle per (device, stream).  Every *_dev call is asynchronous on the stream passed in (cudaStream_t as void*).
+ *
+ * There is no CPU fallback: every compute entry point fails with A3D_ERR_NO_DEVICE when no sm_100 GPU is present.
+ */
+#ifndef A3D_H_
+#define A3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_ABI_VERSION 1
+#define A3D_MAX_LAYERS 8
+#define A3D_VOXELS 262144 /* 64^3, output grid of the reference decoder (autoencoder3D.py:17) */
+
+typedef enum {
+  A3D_OK = 0,
+  A3D_ERR_INVALID = -1,     /* bad argument / unsupported structure */
+  A3D_ERR_CUDA = -2,        /* CUDA runtime/driver error (sticky)    */
+  A3D_ERR_NO_DEVICE = -3,   /* no sm_100 device: there is no CPU path */
+  A3D_ERR_WEIGHTS = -4,     /* weights missing or of the wrong size  */
+  A3D_ERR_WORKSPACE = -5    /* request exceeds the arena             */
+} a3d_status;
+
+enum { A3D_ACT_NONE = 0, A3D_ACT_ELU = 1, A3D_ACT_RELU = 2, A3D_ACT_LRELU = 3 };
+enum { A3D_FINAL_NONE = 0, A3D_FINAL_SIGMOID = 1 };
+enum { A3D_DTYPE_F16 = 0, A3D_DTYPE_BF16 = 1 };          /* operand type of the tensor-core layers */
+enum { A3D_IMPL_TCGEN05 = 0, A3D_IMPL_SIMT = 1 };        /* SIMT = CUDA-core kernels, bring-up/diagnostic only */
+enum { A3D_FILL_PRIOR_SAMPLE = 0, A3D_FILL_MEAN = 1, A3D_FILL_NORMAL = 2 };
+
+/* Mirrors the `structure` dict consumed by decoder3D(structure), src/net_core/autoencoder3D.py:104-112. */
+typedef struct {
+  int32_t abi_version;               /* A3D_ABI_VERSION */
+  int32_t latent_dim;                /* structure['input_dim'] */
+  int32_t num_layers;                /* len(filter_num_list) */
+  int32_t filters[A3D_MAX_LAYERS];   /* structure['filter_num_list'] */
+  int32_t ksizes[A3D_MAX_LAYERS];    /* structure['filter_size_list'] */
+  int32_t strides[A3D_MAX_LAYERS];   /* structure['strides_list'] */
+  int32_t out_grid;                  /* structure['output_shape'][0] (cubic) */
+  int32_t activation;                /* A3D_ACT_*   (structure['activation']) */
+  int32_t final_activation;          /* A3D_FINAL_* (structure['final_activation']) */
+  int32_t device;                    /* CUDA ordinal */
+  int32_t max_chunk;                 /* decodes resident in the arena at once (multiple of 32) */
+  int32_t operand_dtype;             /* A3D_DTYPE_* */
+  int32_t impl;                      /* A3D_IMPL_* */
+} a3d_desc;
+
+typedef struct a3d_handle a3d_handle;
+
+/* decoder3D(structure) -> model            src/net_core/autoencoder3D.py:104-139 (graph construction). */
+int a3d_create(const a3d_desc* desc, a3d_handle** out);
+void a3d_destroy(a3d_handle* h);
+
+/* Number / element count of the Keras variables in model.get_weights() order (27 for the stock decoder). */
+int a3d_num_weights(const a3d_handle* h);
+int64_t a3d_weight_numel(const a3d_handle* h, int index);
+
+/* model.set_weights()/get_weights()/load_weights()   src/module/nolbo.py:1572-1574,1585-1592.
+ * `host` is fp32 in the Keras layout of that variable (Dense [D,512]; ConvT [k,k,k,Cout,Cin]; BN vectors).
+ * Synchronous.  BN folding, operand conversion and per-tap repacking happen lazily before the next decode. */
+int a3d_set_weight(a3d_handle* h, int index, const float* host, size_t nbytes);
+int a3d_get_weight(const a3d_handle* h, int index, float* host, size_t nbytes);
+
+/* decoder(z, training=False)               src/module/nolbo.py:1496,1520; src/module/nolbo_test.py:176,180.
+ * z_dev: [n, latent_dim] fp32 on the device; prob_dev: [n, 64,64,64,1] fp32 (NDHWC, like the Keras output). */
+int a3d_decode(a3d_handle* h, const float* z_dev, int64_t n, float* prob_dev, void* stream);
+
+/* sampling() + mask / fill logic           src/module/function.py:35-38; src/module/nolbo.py:1472-1486 (mean fill),
+ * :1505-1510 (nearest-prior sample fill), :431-439 (N(0,1) fill).  K Philox4x32-10 normal draws per object are
+ * scattered into the missing dims.  z, mask: [B, D]; mu_table: [C, D] (category_vectors); z_out: [B, K, D];
+ * cstar_out: [B] int32 or NULL.  Counter = (dim/4, k, obj_offset + b); key = seed. */
+int a3d_impute(a3d_handle* h, const float* z_dev, const float* mask_dev, const float* mu_table_dev, int C,
+               int64_t B, int K, uint64_t seed, uint64_t obj_offset, int fill_mode, float* z_out_dev,
+               int32_t* cstar_out_dev, void* stream);
+
+/* K-sample anytime reconstruction + scoring: decoder over all B*K completed latents, mean of the K post-sigmoid
+ * grids (src/module/nolbo_test.py:167-177), threshold `>= thr` and TP/FP/FN (src/module/function.py:100-115).
+ * z_bkd_dev: [B, K, D] fp32; target_bits_dev: [B, 32768] bytes, voxel v -> bit (v & 7) of byte v >> 3, v in NDHW
+ * order; counts_dev: [B, 3] int64 (TP, FP, FN), overwritten; mean_prob_dev: [B, 262144] fp32 or NULL. */
+int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev,
+                     float thr, int64_t* counts_dev, float* mean_prob_dev, void* stream);
+
+/* voxelPrecisionRecall(xTarget, xPred, prob)   src/module/function.py:100-115.  Both [B, V] fp32 on the device;
+ * counts_dev [B, 3] int64 = TP, FP, FN with yPred = (xPred >= thr), yTarget = (xTarget > 0.5). */
+int a3d_counts(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V, float thr,
+               int64_t* counts_dev, void* stream);
+
+/* Bit-pack fp32 {0,1} targets [B, V] (loader layout, src/dataset_loader/pascal3D.py:149-152) to [B, V/8] bytes. */
+int a3d_pack_targets(a3d_handle* h, const float* target_dev, int64_t B, int64_t V, uint8_t* bits_dev, void* stream);
+
+/* End-to-end call with HOST buffers (what a getEval-style caller holds, src/module/nolbo.py:1449-1528): copies
+ * z / mask / mu_table / packed targets host->device, imputes, decodes, scores, copies counts (and the mean grid if
+ * requested) back and synchronises.  Host buffers may be pageable or pinned. */
+int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, const float* mu_table, int C, int64_t B,
+                          int K, uint64_t seed, uint64_t obj_offset, int fill_mode, const uint8_t* target_bits,
+                          float thr, int64_t* counts, float* mean_prob_or_null);
+
+/* Bytes of device memory the arena holds / would need for `n` resident decodes. */
+size_t a3d_workspace_bytes(const a3d_handle* h, int64_t n);
+
+/* Diagnostics for per-layer parity tests: copy hidden layer `layer` (0 = dense output [n,4,4,4,8], 1..4 = ConvT
+ * outputs, NDHWC) of the most recent chunk to `host` as fp32.  Synchronous. */
+int a3d_debug_read_layer(a3d_handle* h, int layer, int64_t n, float* host, size_t nbytes);
+
+/* Kernel launches issued by this handle since creation (what bench.py reports as gpu_launches). */
+int64_t a3d_launch_count(const a3d_handle* h);
+
+/* Device-side time of the last a3d_decode / a3d_anytime_eval per stage, in ms, when profiling was enabled with
+ * a3d_set_profiling(h, 1): stages = dense+L1, L2, L3, L4, tail.  Returns number of stages written. */
+int a3d_set_profiling(a3d_handle* h, int enable);
+int a3d_stage_times_ms(a3d_handle* h, float* out, int max_stages);
+
+const char* a3d_last_error(void);
+int a3d_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3D_H_ */
