@@ -14,9 +14,11 @@
 // delta_w via the start address of the UMMA shared-memory descriptor.  The out-of-bounds fill of TMA is the
 // 'same' padding.  delta_w = 0 feeds both pw parities in a single MMA of N = 2*COUT.
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue
-// (tcgen05.ld -> scale/shift -> activation -> 16-bit -> global).  Accumulators are double-buffered in TMEM so the
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = epilogue
+// (tcgen05.ld -> scale/shift -> activation -> 16-bit -> global; warps e and e+4 split the columns).  Accumulators are double-buffered in TMEM so the
 // epilogue of unit i overlaps the main loop of unit i + 1.  Persistent CTAs, static round-robin unit schedule.
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -47,11 +49,22 @@ struct Cfg {
   static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
 };
 
-__device__ __forceinline__ float activate(float v, int act) {
-  if (act == A3D_ACT_ELU) return v > 0.f ? v : expm1f(v);
-  if (act == A3D_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == A3D_ACT_LRELU) return v > 0.f ? v : 0.3f * v;
-  return v;
+// ELU(alpha = 1) without the slow expm1f: ex2.approx for v <= -1/8 (|rel err| ~ 2e-6), degree-5 Taylor of expm1 for
+// -1/8 < v < 0 (truncation error < 6e-9); branch-free.
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if constexpr (ACT == A3D_ACT_ELU) {
+    const float e = __expf(v) - 1.f;
+    const float p = v * fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+    const float neg = v > -0.125f ? p : e;
+    return v > 0.f ? v : neg;
+  } else if constexpr (ACT == A3D_ACT_RELU) {
+    return fmaxf(v, 0.f);
+  } else if constexpr (ACT == A3D_ACT_LRELU) {
+    return v > 0.f ? v : 0.3f * v;
+  } else {
+    return v;
+  }
 }
 
 template <int FMT>
@@ -65,11 +78,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-template <class C, int FMT>
-__global__ void __launch_bounds__(256, 1)
+constexpr int kEpiWarps = 8;                 // 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+
+template <class C, int FMT, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
 convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
                    uint16_t* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int n_blocks, int n_alloc, int act) {
+                   int n_blocks, int n_alloc, int dbg) {
   constexpr int CIN = C::CIN, COUT = C::COUT, WIN = C::WIN, NT = C::NT, NACC = C::NACC;
   (void)CIN;
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +100,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint64_t* t_full = b_empty + C::B_STAGES;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned: bars are 8 B, +16 B slot
   float* s_shift = s_scale + NACC;
 
   const int warp = threadIdx.x >> 5;
@@ -98,7 +114,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::B_STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 32 * kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -229,11 +245,15 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: TMEM -> BN/act -> 16-bit -> global
-    const int row = threadIdx.x - 128;                 // TMEM lane == GEMM row
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int e = warp - 4;
+    const int quarter = e & 3;                         // TMEM lane quarter this warp may read (== warp % 4)
+    const int chalf = e >> 2;                          // which half of the accumulator columns
+    const int row = quarter * 32 + lane;               // TMEM lane == GEMM row
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int w = row / NT;
     const int nloc = row % NT;
     constexpr int OD = 2 * WIN;
+    constexpr int NCOLS = NACC / 2;                    // columns per warp
     uint32_t unit_it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
       const int par = u % C::NPAR;
@@ -245,27 +265,31 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       const int n = nb * NT + nloc;
       ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + lane_base + buf * NACC;
+      const uint32_t tacc = tmem_base + lane_base + buf * NACC + chalf * NCOLS;
 #pragma unroll 1
-      for (int g = 0; g < NACC / 32; ++g) {
-        uint32_t v0[16], v1[16];
-        ptx::tmem_ld16(tacc + g * 32, v0);
-        ptx::tmem_ld16(tacc + g * 32 + 16, v1);
+      for (int g = 0; g < NCOLS / 32; ++g) {
+        uint32_t v[32];
+        ptx::tmem_ld16(tacc + g * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        ptx::tmem_ld16(tacc + g * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         ptx::tmem_ld_wait();
-        const int col = g * 32;
+        const int col = chalf * NCOLS + g * 32;
         const int pw = C::PWB ? (col / COUT) : (par & 1);
         const int co = col % COUT;
         uint32_t o[16];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float x0 = __uint_as_float(v0[2 * i]) * s_scale[col + 2 * i] + s_shift[col + 2 * i];
-          float x1 = __uint_as_float(v0[2 * i + 1]) * s_scale[col + 2 * i + 1] + s_shift[col + 2 * i + 1];
-          o[i] = pack2<FMT>(activate(x0, act), activate(x1, act));
-          float y0 = __uint_as_float(v1[2 * i]) * s_scale[col + 16 + 2 * i] + s_shift[col + 16 + 2 * i];
-          float y1 = __uint_as_float(v1[2 * i + 1]) * s_scale[col + 16 + 2 * i + 1] + s_shift[col + 16 + 2 * i + 1];
-          o[8 + i] = pack2<FMT>(activate(y0, act), activate(y1, act));
+          const float4 sc = sc4[i], sh = sh4[i];
+          float x0 = fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x);
+          float x1 = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
+          float x2 = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
+          float x3 = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
+          if (!(dbg & 2)) { x0 = activate<ACT>(x0); x1 = activate<ACT>(x1); x2 = activate<ACT>(x2); x3 = activate<ACT>(x3); }
+          o[2 * i] = pack2<FMT>(x0, x1);
+          o[2 * i + 1] = pack2<FMT>(x2, x3);
         }
-        if (n < n_alloc) {
+        if (n < n_alloc && !(dbg & 1)) {
           const size_t vox = (((size_t)n * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * w + pw);
           uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + co);
           dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -292,15 +316,28 @@ int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fm
   int grid = num_sms < total_units ? num_sms : total_units;
   // keep the parity class of a CTA fixed across its units (weights of one class stay hot in L2 / same rows)
   if (grid > C::NPAR) grid -= grid % C::NPAR;
+  static const int dbg = getenv("A3D_DEBUG_FLAGS") ? atoi(getenv("A3D_DEBUG_FLAGS")) : 0;
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    kern<<<grid, 256, C::SMEM_BYTES, st>>>(L.tmap_act, L.tmap_wgt, reinterpret_cast<uint16_t*>(out), L.scale, L.shift,
-                                           n_blocks, (int)n_alloc, act);
+    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(L.tmap_act, L.tmap_wgt, reinterpret_cast<uint16_t*>(out), L.scale,
+                                                L.shift, n_blocks, (int)n_alloc, dbg);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };
-  if (fmt == A3D_DTYPE_F16) return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16>);
-  return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16>);
+  if (fmt == A3D_DTYPE_F16) {
+    switch (act) {
+      case A3D_ACT_ELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16, A3D_ACT_ELU>);
+      case A3D_ACT_RELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16, A3D_ACT_RELU>);
+      case A3D_ACT_LRELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16, A3D_ACT_LRELU>);
+      default: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_F16, A3D_ACT_NONE>);
+    }
+  }
+  switch (act) {
+    case A3D_ACT_ELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16, A3D_ACT_ELU>);
+    case A3D_ACT_RELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16, A3D_ACT_RELU>);
+    case A3D_ACT_LRELU: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16, A3D_ACT_LRELU>);
+    default: return launch(convt_s2_tc_kernel<C, A3D_DTYPE_BF16, A3D_ACT_NONE>);
+  }
 }
 
 }  // namespace

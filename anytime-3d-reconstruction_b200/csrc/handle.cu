@@ -76,6 +76,8 @@ struct a3d_handle {
   void* d_w1_tco = nullptr; float *d_s1 = nullptr, *d_h1 = nullptr;          // stride-1 layer
   ConvLayer conv[3];                                                           // stride-2 hidden layers
   float* d_w5 = nullptr;                                                       // final kernel [tap][ci] fp32
+  void* d_w5_16 = nullptr;                                                     // same, operand dtype (tcgen05 tail)
+  CUtensorMap tmap_a4, tmap_w5;                                                // tail: (c,w,h,d,n) view of act[4]; W5
   // arena
   int64_t max_chunk = 0;
   void* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // a0..a4
@@ -256,6 +258,27 @@ int finalize_weights(a3d_handle* h) {
   }
   // final kernel [4,4,4,1,64] is already [tap][ci]
   if ((rc = upload(h->w[26].data(), h->w[26].size() * 4, (void**)&h->d_w5))) return rc;
+  {
+    p16.resize(h->w[26].size());
+    for (size_t i = 0; i < p16.size(); ++i) p16[i] = cvt16(h->w[26][i], fmt);
+    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_16))) return rc;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return A3D_ERR_CUDA; }
+    const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    cuuint64_t dims[5] = {64, 32, 32, 32, (cuuint64_t)h->max_chunk};   // (c, w, h, d, n)
+    cuuint64_t strides[4] = {128, 128 * 32, 128 * 32 * 32, 128ull * 32 * 32 * 32};
+    cuuint32_t box[5] = {64, 8, 8, 8, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&h->tmap_a4, dt, 5, h->act[4], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    cuuint64_t wd[2] = {64, 64};
+    cuuint64_t ws[1] = {128};
+    cuuint32_t wb[2] = {64, 64};
+    r = enc(&h->tmap_w5, dt, 2, h->d_w5_16, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+  }
   h->dirty = false;
   return A3D_OK;
 }
@@ -284,6 +307,15 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
   }
   h->last_chunk_n = n;
   return A3D_OK;
+}
+
+int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, unsigned long long* counts, float* mean,
+             cudaStream_t st) {
+  const int sig = h->desc.final_activation == A3D_FINAL_SIGMOID;
+  if (h->desc.impl == A3D_IMPL_SIMT)
+    return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, st, &h->launches);
+  return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, h->num_sms, st,
+                        &h->launches);
 }
 
 void collect_profile(a3d_handle* h, cudaStream_t st, bool first) {
@@ -371,7 +403,7 @@ void a3d_destroy(a3d_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
-  cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5);
+  cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16);
   for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
@@ -434,8 +466,7 @@ int a3d_decode(a3d_handle* h, const float* z_dev, int64_t n, float* prob_dev, vo
   for (int64_t off = 0; off < n; off += h->max_chunk) {
     const int64_t nc = (n - off < h->max_chunk) ? n - off : h->max_chunk;
     if ((rc = sticky(h, run_hidden(h, z_dev + off * D, nc, st)))) return rc;
-    rc = launch_tail(h->act[4], h->d_w5, nc, 1, h->desc.operand_dtype, h->desc.final_activation == A3D_FINAL_SIGMOID,
-                     nullptr, 0.5f, nullptr, prob_dev + off * (int64_t)A3D_VOXELS, st, &h->launches);
+    rc = run_tail(h, nc, 1, nullptr, 0.5f, nullptr, prob_dev + off * (int64_t)A3D_VOXELS, st);
     if ((rc = sticky(h, rc))) return rc;
     collect_profile(h, st, off == 0);
   }
@@ -477,10 +508,9 @@ int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, co
   for (int64_t b0 = 0; b0 < B; b0 += obj_per_chunk) {
     const int64_t nb = (B - b0 < obj_per_chunk) ? B - b0 : obj_per_chunk;
     if ((rc = sticky(h, run_hidden(h, z_bkd_dev + b0 * K * D, nb * K, st)))) return rc;
-    rc = launch_tail(h->act[4], h->d_w5, nb, K, h->desc.operand_dtype, h->desc.final_activation == A3D_FINAL_SIGMOID,
-                     target_bits_dev ? target_bits_dev + b0 * (A3D_VOXELS / 8) : nullptr, thr,
-                     counts_dev ? reinterpret_cast<unsigned long long*>(counts_dev) + b0 * 3 : nullptr,
-                     mean_prob_dev ? mean_prob_dev + b0 * (int64_t)A3D_VOXELS : nullptr, st, &h->launches);
+    rc = run_tail(h, nb, K, target_bits_dev ? target_bits_dev + b0 * (A3D_VOXELS / 8) : nullptr, thr,
+                  counts_dev ? reinterpret_cast<unsigned long long*>(counts_dev) + b0 * 3 : nullptr,
+                  mean_prob_dev ? mean_prob_dev + b0 * (int64_t)A3D_VOXELS : nullptr, st);
     if ((rc = sticky(h, rc))) return rc;
     collect_profile(h, st, b0 == 0);
   }

@@ -47,6 +47,9 @@ int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t 
 int launch_tail(const void* a4, const float* w5, int64_t B, int K, int fmt, int final_sigmoid,
                 const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob,
                 cudaStream_t st, int64_t* launches);
+int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64_t B, int K, int fmt,
+                   int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
+                   float* mean_prob, int num_sms, cudaStream_t st, int64_t* launches);
 int launch_impute(const float* z, const float* mask, const float* mu, int C, int64_t B, int K, int D, uint64_t seed,
                   uint64_t obj_offset, int fill, float* z_out, int32_t* cstar, cudaStream_t st, int64_t* launches);
 int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, float thr,

@@ -59,7 +59,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef A3D_MBAR_TIMEOUT_CYCLES
 #define A3D_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
-__device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
   printf("a3d: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar,
          parity);
   __trap();
