@@ -172,6 +172,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       uint32_t a_it = 0, b_it = 0, unit_it = 0;
       constexpr uint32_t idesc_full = ptx::make_idesc_f16(128, NACC > 256 ? 256 : NACC, FMT);
       constexpr uint32_t idesc_half = ptx::make_idesc_f16(128, COUT, FMT);
+      const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
+      const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
       for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
         const int par = u % C::NPAR;
         const int pos = u / C::NPAR;
@@ -193,42 +195,39 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             for (int c = 0; c < C::CHUNKS; ++c) {
               const int as = a_it % C::A_STAGES;
               ptx::mbar_wait(&a_full[as], (a_it / C::A_STAGES) & 1);
-              const uint32_t a_addr = ptx::smem_u32(smem_a + as * C::A_BYTES);
+              const uint32_t a_lo = a_lo0 + as * (C::A_BYTES >> 4);
 #pragma unroll
               for (int j = 0; j < C::BSLOTS; ++j) {
                 const int bs = b_it % C::B_STAGES;
                 ptx::mbar_wait(&b_full[bs], (b_it / C::B_STAGES) & 1);
                 ptx::tc_fence_after();
-                const uint32_t b_addr = ptx::smem_u32(smem_b + bs * C::B_BYTES);
+                const uint32_t b_lo = b_lo0 + bs * (C::B_BYTES >> 4);
+                constexpr uint32_t W1 = (NT * 128) >> 4;       // one position along w, in 16-byte units
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                  const uint32_t ko = kk * 32;  // 16 elements * 2 bytes inside the 128-byte swizzled row
+                  const uint32_t ko = kk * 2;  // 16 elements * 2 bytes inside the 128-byte swizzled row, >> 4
                   if constexpr (C::PWB && C::BSLOTS == 1) {
                     // COUT = 64: [0,128) = (pw0,tw1 | pw1,tw2) dw=0; [128,192) = pw0,tw3 dw=-1; [192,256) = pw1,tw0 dw=+1
-                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + NT * 128 + ko, 1024),
-                                     ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
                     accum = 1;
-                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + ko, 1024),
-                                     ptx::make_sw128_kmajor_desc(b_addr + 2 * COUT * 128 + ko, 1024), idesc_half, 1);
-                    ptx::umma_f16<1>(tacc + COUT, ptx::make_sw128_kmajor_desc(a_addr + 2 * NT * 128 + ko, 1024),
-                                     ptx::make_sw128_kmajor_desc(b_addr + 3 * COUT * 128 + ko, 1024), idesc_half, 1);
+                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ((2 * COUT * 128) >> 4) + ko),
+                                     idesc_half, 1);
+                    ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
+                                     ptx::sw128_desc(b_lo + ((3 * COUT * 128) >> 4) + ko), idesc_half, 1);
                   } else if constexpr (C::PWB) {
                     // COUT = 128: slot 0 = (pw0,tw1 | pw1,tw2) dw=0 (N = 256); slot 1 = pw0,tw3 dw=-1 | pw1,tw0 dw=+1
                     if (j == 0) {
-                      ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + NT * 128 + ko, 1024),
-                                       ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
                       accum = 1;
                     } else {
-                      ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + ko, 1024),
-                                       ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_half, 1);
-                      ptx::umma_f16<1>(tacc + COUT, ptx::make_sw128_kmajor_desc(a_addr + 2 * NT * 128 + ko, 1024),
-                                       ptx::make_sw128_kmajor_desc(b_addr + COUT * 128 + ko, 1024), idesc_half, 1);
+                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ko), idesc_half, 1);
+                      ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
+                                       ptx::sw128_desc(b_lo + ((COUT * 128) >> 4) + ko), idesc_half, 1);
                     }
                   } else {
                     // COUT = 256, one pw per unit: slot 0 = dw=0 tap, slot 1 = dw=+-1 tap
-                    const uint32_t a_off = (j == 0) ? NT * 128 : (pw ? 2 * NT * 128 : 0);
-                    ptx::umma_f16<1>(tacc, ptx::make_sw128_kmajor_desc(a_addr + a_off + ko, 1024),
-                                     ptx::make_sw128_kmajor_desc(b_addr + ko, 1024), idesc_full, accum);
+                    const uint32_t a_off = (j == 0) ? W1 : (pw ? 2 * W1 : 0);
+                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + a_off + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
                     accum = 1;
                   }
                 }

@@ -191,6 +191,11 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, u
   d |= (uint64_t)2 << 61;                            // [61,64) layout type 2 = SWIZZLE_128B
   return d;
 }
+// Same descriptor split for cheap per-MMA updates: the high word is constant for a layout, the low word is
+// (start_address >> 4) | (1 << 16); advancing the start address by X bytes (X % 16 == 0) adds X >> 4 to the low word.
+constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t lo) { return ((uint64_t)kSw128DescHi << 32) | lo; }
 // Instruction descriptor for kind::f16: fp32 accumulate, both operands K-major, format 0 = f16 / 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |

@@ -28,28 +28,30 @@ __global__ void dense_kernel(const float* __restrict__ z, int D, const float* __
 
 // ---------------------------------------------------------------------------------------------------------
 // ConvT3D k=4 s=1 'same' (pad 1 before / 2 after): out[o, co] = sum_{t, ci} in[o - t + 1, ci] * W[t, co, ci].
-// 4^3 x 8 -> 4^3 x 512.  Block = NB decodes x 512 output channels; weights [tap][ci][co] read once per NB decodes.
+// 4^3 x 8 -> 4^3 x 512.  Block = NB decodes; thread = 2 adjacent output channels x NB decodes (register tile); the
+// input voxels sit in shared memory as [pos][ci][NB] so one (pos, ci) is NB/4 broadcast LDS.128; weights [tap][ci][co]
+// are read once per NB decodes as packed 16-bit pairs.
 template <int FMT, int NB>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 convt_s1_kernel(const uint16_t* __restrict__ a0, const uint16_t* __restrict__ w_tco, const float* __restrict__ scale,
-                const float* __restrict__ shift, uint16_t* __restrict__ a1, int64_t n_total, int cin, int cout,
-                int act) {
-  extern __shared__ float xs[];  // [NB][64 pos][cin]
+                const float* __restrict__ shift, uint16_t* __restrict__ a1, int64_t n_total, int act) {
+  constexpr int CIN = 8, COUT = 512;
+  __shared__ __align__(16) float xs[64 * CIN * NB];  // [pos][ci][b]
   const int64_t n0 = (int64_t)blockIdx.x * NB;
-  const int per = 64 * cin;
-  for (int i = threadIdx.x; i < NB * per; i += blockDim.x) {
-    const int64_t n = n0 + i / per;
-    xs[i] = n < n_total ? to_f32<FMT>(a0[n * per + i % per]) : 0.f;
+  for (int i = threadIdx.x; i < NB * 64 * CIN; i += blockDim.x) {
+    const int b = i / (64 * CIN), pc = i % (64 * CIN);
+    const int64_t n = n0 + b;
+    xs[pc * NB + b] = n < n_total ? to_f32<FMT>(a0[n * (64 * CIN) + pc]) : 0.f;
   }
   __syncthreads();
-  const int co = threadIdx.x;
-  if (co >= cout) return;
-  const float sc = scale[co], sh = shift[co];
+  const int co = threadIdx.x * 2;
+  const float sc0 = scale[co], sc1 = scale[co + 1], sh0 = shift[co], sh1 = shift[co + 1];
+  const uint32_t* w32 = reinterpret_cast<const uint32_t*>(w_tco);
   for (int o = 0; o < 64; ++o) {
     const int od = o >> 4, oh = (o >> 2) & 3, ow = o & 3;
-    float acc[NB];
+    float acc0[NB], acc1[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int b = 0; b < NB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
     for (int td = 0; td < 4; ++td) {
       const int id = od - td + 1;
       if (id < 0 || id > 3) continue;
@@ -61,10 +63,18 @@ convt_s1_kernel(const uint16_t* __restrict__ a0, const uint16_t* __restrict__ w_
           if (iw < 0 || iw > 3) continue;
           const int tap = (td * 4 + th) * 4 + tw;
           const int ipos = (id * 4 + ih) * 4 + iw;
-          for (int ci = 0; ci < cin; ++ci) {
-            const float wv = to_f32<FMT>(w_tco[((size_t)tap * cin + ci) * cout + co]);
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = fmaf(xs[b * per + ipos * cin + ci], wv, acc[b]);
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float2 wv = unpack2<FMT>(__ldg(w32 + (((size_t)tap * CIN + ci) * COUT + co) / 2));
+            const float4* xp = reinterpret_cast<const float4*>(xs + (ipos * CIN + ci) * NB);
+#pragma unroll
+            for (int q = 0; q < NB / 4; ++q) {
+              const float4 x = xp[q];
+              acc0[4 * q + 0] = fmaf(x.x, wv.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(x.x, wv.y, acc1[4 * q + 0]);
+              acc0[4 * q + 1] = fmaf(x.y, wv.x, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(x.y, wv.y, acc1[4 * q + 1]);
+              acc0[4 * q + 2] = fmaf(x.z, wv.x, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(x.z, wv.y, acc1[4 * q + 2]);
+              acc0[4 * q + 3] = fmaf(x.w, wv.x, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(x.w, wv.y, acc1[4 * q + 3]);
+            }
           }
         }
       }
@@ -72,7 +82,11 @@ convt_s1_kernel(const uint16_t* __restrict__ a0, const uint16_t* __restrict__ w_
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const int64_t n = n0 + b;
-      if (n < n_total) a1[(n * 64 + o) * cout + co] = from_f32<FMT>(apply_act(acc[b] * sc + sh, act));
+      if (n < n_total) {
+        const uint32_t v = (uint32_t)from_f32<FMT>(apply_act(acc0[b] * sc0 + sh0, act)) |
+                           ((uint32_t)from_f32<FMT>(apply_act(acc1[b] * sc1 + sh1, act)) << 16);
+        *reinterpret_cast<uint32_t*>(a1 + (n * 64 + o) * COUT + co) = v;
+      }
     }
   }
 }
@@ -127,17 +141,16 @@ int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const flo
                     const float* h0, void* a0, const void* w1_tco, const float* s1, const float* h1, void* a1,
                     int fmt, int act, cudaStream_t st, int64_t* launches) {
   if (n <= 0) return A3D_OK;
-  constexpr int NB = 8;
+  constexpr int NB = 16;
   const int blocks1 = (int)((n + NB - 1) / NB);
-  const size_t smem1 = (size_t)NB * 64 * 8 * sizeof(float);
   if (fmt == A3D_DTYPE_F16) {
     dense_kernel<A3D_DTYPE_F16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
-    convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 512, smem1, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
-                                                                   (uint16_t*)a1, n, 8, 512, act);
+    convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+                                                               (uint16_t*)a1, n, act);
   } else {
     dense_kernel<A3D_DTYPE_BF16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
-    convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 512, smem1, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
-                                                                    (uint16_t*)a1, n, 8, 512, act);
+    convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+                                                                (uint16_t*)a1, n, act);
   }
   A3D_CUDA_OK(cudaGetLastError());
   if (launches) *launches += 2;

@@ -102,7 +102,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, FMT);
       ptx::mbar_wait(w_full, 0);
-      const uint32_t w_addr = ptx::smem_u32(smem_w);
+      const uint32_t w_lo = ptx::sw128_desc_lo(ptx::smem_u32(smem_w));
+      const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
       uint32_t it = 0;
       for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
         for (int k = 0; k < K; ++k, ++it) {
@@ -110,14 +111,13 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           ptx::mbar_wait(&t_empty[s], ((it >> 1) & 1) ^ 1);
           ptx::mbar_wait(&a_full[s], (it >> 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + s * kABytes);
+          const uint32_t a_lo = a_lo0 + s * (kABytes >> 4);
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              ptx::umma_f16<1>(tmem_base + s * 256 + m * 64,
-                               ptx::make_sw128_kmajor_desc(a_addr + m * 16384 + kk * 32, 1024),
-                               ptx::make_sw128_kmajor_desc(w_addr + kk * 32, 1024), idesc, kk > 0);
+              ptx::umma_f16<1>(tmem_base + s * 256 + m * 64, ptx::sw128_desc(a_lo + m * (16384 >> 4) + kk * 2),
+                               ptx::sw128_desc(w_lo + kk * 2), idesc, kk > 0);
             }
           }
           ptx::umma_commit<1>(&a_empty[s]);

@@ -36,14 +36,25 @@ def conv3d_transpose_same(x: np.ndarray, w: np.ndarray, stride: int) -> np.ndarr
     x = np.asarray(x, np.float64)
     w = np.asarray(w, np.float64)
     k = w.shape[0]
-    Rd = same_forward_relation(x.shape[1] * stride, k, stride)
-    Rh = same_forward_relation(x.shape[2] * stride, k, stride)
-    Rw = same_forward_relation(x.shape[3] * stride, k, stride)
-    assert Rd.shape[0] == x.shape[1]
-    # contract one axis at a time to keep intermediates small
-    # t1[n, a,b,c, td,th,tw, co] would be large; instead scatter axis by axis with the kernel folded in last.
-    # y[n, D, H, W, co] = sum x[n,a,b,c,ci] Rd[a,p,D] Rh[b,q,H] Rw[c,r,W] w[p,q,r,co,ci]
-    return np.einsum('nabci,apD,bqH,crW,pqroi->nDHWo', x, Rd, Rh, Rw, w, optimize=True)
+    n, d, h, wd, _ = x.shape
+    Rd = same_forward_relation(d * stride, k, stride)
+    Rh = same_forward_relation(h * stride, k, stride)
+    Rw = same_forward_relation(wd * stride, k, stride)
+    assert Rd.shape[0] == d and Rh.shape[0] == h and Rw.shape[0] == wd
+    out = np.zeros((n, d * stride, h * stride, wd * stride, w.shape[3]), np.float64)
+    # y[n, D, H, W, co] = sum x[n,a,b,c,ci] Rd[a,p,D] Rh[b,q,H] Rw[c,r,W] w[p,q,r,co,ci], one tap (p,q,r) at a time:
+    # the relation tensors give, per tap, the (input index, output index) pairs that the forward conv couples.
+    for p in range(k):
+        ad, jd = np.nonzero(Rd[:, p, :])
+        for q in range(k):
+            ah, jh = np.nonzero(Rh[:, q, :])
+            for r in range(k):
+                aw, jw = np.nonzero(Rw[:, r, :])
+                if len(ad) == 0 or len(ah) == 0 or len(aw) == 0:
+                    continue
+                y = x[:, ad][:, :, ah][:, :, :, aw] @ w[p, q, r].T      # [n, |ad|, |ah|, |aw|, co]
+                out[np.ix_(np.arange(n), jd, jh, jw, np.arange(w.shape[3]))] += y
+    return out
 
 
 def batchnorm(x, gamma, beta, mean, var):

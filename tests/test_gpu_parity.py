@@ -1,0 +1,300 @@
+"""GPU parity tests (-m gpu): the sm_100a CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+identical weights, latents and masks.
+
+Tolerances (BASELINE.json north_star): occupancy probabilities within 1e-2 max-abs, fewer than 0.1 % of thresholded
+voxels differing; integer / index work (Philox words -> masks, counts, packing) bit-exact; Box-Muller normals within
+5e-6 absolute (fp32 logf/sincospif vs the fp64 evaluation of the same fp32 uniforms)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import anytime_ref as ar, decoder_ref as dr
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2       # max |p_gpu - p_oracle|
+FLIP_TOL = 1e-3       # fraction of voxels on the other side of the 0.5 threshold
+NORMAL_TOL = 5e-6
+
+
+@pytest.fixture(scope='module')
+def a3d_mod():
+    import a3d
+    return a3d
+
+
+@pytest.fixture(scope='module')
+def weights():
+    return {
+        ('mn', 'default'): dr.keras_default_weights(dr.MODELNET_DECODER, 101),
+        ('mn', 'trained'): dr.trained_like_weights(dr.MODELNET_DECODER, 102),
+        ('pa', 'trained'): dr.trained_like_weights(dr.PASCAL_DECODER, 103),
+    }
+
+
+@pytest.fixture(scope='module')
+def decoders(a3d_mod, weights):
+    out = {}
+    for (ds, kind), ws in weights.items():
+        st = dr.MODELNET_DECODER if ds == 'mn' else dr.PASCAL_DECODER
+        d = a3d_mod.decoder3D(st, max_chunk=64)
+        d.set_weights(ws)
+        out[(ds, kind)] = d
+    return out
+
+
+def flips(a, b, thr=0.5):
+    return float(((a >= thr) != (b >= thr)).mean())
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+@pytest.mark.parametrize('key', [('mn', 'default'), ('mn', 'trained'), ('pa', 'trained')])
+def test_decoder_matches_golden_fixture(golden, decoders, key):
+    tag = f'{key[0]}_{key[1]}'
+    dec = decoders[key]
+    out = dec(golden[f'{tag}_z'])
+    assert out.shape == (2, 64, 64, 64, 1) and out.dtype == np.float32
+    flat = out.reshape(2, -1)
+    assert np.abs(flat[:, golden['sample_idx']] - golden[f'{tag}_prob_samples']).max() < PROB_TOL
+    gbits = np.unpackbits(golden[f'{tag}_bits'], axis=1, bitorder='little')
+    assert ((flat >= 0.5) != gbits.astype(bool)).mean() < FLIP_TOL
+
+
+@pytest.mark.parametrize('key', [('mn', 'default'), ('mn', 'trained'), ('pa', 'trained')])
+def test_decoder_per_layer_and_end_to_end_vs_oracle(decoders, weights, key):
+    dec, ws = decoders[key], weights[key]
+    st = dec.structure
+    rng = np.random.default_rng(7)
+    n = 5     # ragged: not a multiple of any tile size
+    z = dr.round_bf16(rng.standard_normal((n, st['input_dim'])).astype(np.float32))
+    ref, layers = dr.decoder_forward(st, ws, z, return_layers=True)
+    out = dec(z)
+    for li in range(5):
+        g = dec.debug_layer(li, n)
+        r = layers[li].numpy()
+        rel = np.sqrt(((g - r) ** 2).mean()) / np.sqrt((r ** 2).mean())
+        assert rel < 2e-3, f'layer {li}: relative RMS error {rel}'
+        assert np.abs(g - r).max() < 4e-3 * max(1.0, np.abs(r).max()), f'layer {li}'
+    ref = ref.numpy()
+    assert np.abs(out - ref).max() < PROB_TOL
+    assert flips(out, ref) < FLIP_TOL
+
+
+def test_decoder_call_surface(a3d_mod, decoders, weights):
+    dec = decoders[('mn', 'trained')]
+    with pytest.raises(NotImplementedError):
+        dec(np.zeros((1, 64), np.float32), training=True)
+    got = dec.get_weights()
+    assert len(got) == 27 and all(np.array_equal(a, b) for a, b in zip(got, weights[('mn', 'trained')]))
+    with pytest.raises(ValueError):
+        dec.set_weights(got[:-1])
+    bad = [w.copy() for w in got]
+    bad[6] = bad[6][..., :4]
+    with pytest.raises(ValueError):
+        dec.set_weights(bad)
+    z = np.random.default_rng(0).standard_normal((3, 64)).astype(np.float32)
+    a = dec(z)
+    b = dec(torch.from_numpy(z).cuda())
+    assert isinstance(b, torch.Tensor) and b.is_cuda and np.array_equal(a, b.cpu().numpy())
+    assert dec(np.zeros((0, 64), np.float32)).shape == (0, 64, 64, 64, 1)       # empty batch
+    with pytest.raises(RuntimeError, match='unsupported decoder structure'):
+        a3d_mod.decoder3D(dict(dr.MODELNET_DECODER, filter_num_list=[512, 256, 128, 32, 1]))
+    fresh = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32)
+    with pytest.raises(RuntimeError, match='never set'):
+        fresh(z)
+
+
+def test_decoder_batch_and_chunk_invariance(a3d_mod, weights):
+    """Size-independent property: a latent decodes to bit-identical output wherever it sits in a batch / chunk."""
+    ws = weights[('mn', 'trained')]
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((70, 64)).astype(np.float32)
+    small = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32)    # 70 decodes -> 3 chunks
+    big = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=96)      # one chunk
+    small.set_weights(ws)
+    big.set_weights(ws)
+    a = small(torch.from_numpy(z).cuda())
+    b = big(torch.from_numpy(z).cuda())
+    assert torch.equal(a, b)
+    c = big(torch.from_numpy(z[::-1].copy()).cuda())
+    assert torch.equal(c.flip(0), b)
+
+
+def test_simt_and_tcgen05_paths_agree(a3d_mod, weights):
+    ws = weights[('mn', 'trained')]
+    z = np.random.default_rng(1).standard_normal((3, 64)).astype(np.float32)
+    t = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32, impl='tcgen05')
+    s = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32, impl='simt')
+    t.set_weights(ws)
+    s.set_weights(ws)
+    a, b = t(z), s(z)
+    assert np.abs(a - b).max() < 5e-3 and flips(a, b) < 2e-4
+
+
+def test_bf16_operands_mode(a3d_mod, weights):
+    ws = weights[('mn', 'trained')]
+    z = dr.round_bf16(np.random.default_rng(2).standard_normal((4, 64)).astype(np.float32))
+    d = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32, operand_dtype='bf16')
+    d.set_weights(ws)
+    out = d(z)
+    ref = dr.decoder_forward(dr.MODELNET_DECODER, ws, z).numpy()
+    assert flips(out, ref) < FLIP_TOL          # bf16 activations: threshold parity holds, probabilities are looser
+    assert np.abs(out - ref).max() < 5e-2
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize('fill', ['prior_sample', 'mean', 'normal'])
+def test_impute_matches_oracle_and_golden(a3d_mod, decoders, golden, fill):
+    dec = decoders[('pa', 'trained')]       # D = 16
+    z, mask, mu = golden['imp_z'], golden['imp_mask'], golden['imp_mu']
+    zo, cs = a3d_mod.impute(dec, z, mask, mu, K=3, seed=4242, obj_offset=7, fill=fill)
+    zo, cs = zo.cpu().numpy(), cs.cpu().numpy()
+    assert np.abs(zo - golden[f'imp_{fill}_z']).max() < NORMAL_TOL
+    assert np.array_equal(cs, golden[f'imp_{fill}_c'])
+    if fill != 'normal':
+        keep = np.broadcast_to(mask[:, None, :] == 1, zo.shape) & np.broadcast_to(z[:, None, :] != 0, zo.shape)
+        assert np.array_equal(zo[keep], np.broadcast_to(z[:, None, :], zo.shape)[keep])   # received dims untouched, bit-exact
+
+
+@pytest.mark.parametrize('B,K,D', [(1, 1, 64), (3, 5, 64), (257, 2, 16), (64, 32, 64)])
+def test_impute_shapes_and_sharding_invariance(a3d_mod, decoders, B, K, D):
+    dec = decoders[('mn', 'trained') if D == 64 else ('pa', 'trained')]
+    rng = np.random.default_rng(B * 100 + K)
+    z = rng.standard_normal((B, D)).astype(np.float32)
+    mask = ar.bernoulli_mask(rng, B, D, 0.6)
+    mu = rng.standard_normal((12, D)).astype(np.float32)
+    zo, cs = a3d_mod.impute(dec, z, mask, mu, K=K, seed=2 ** 40 + 17, obj_offset=2 ** 33, fill='prior_sample')
+    ref, rcs = ar.impute(z, mask, mu, K, seed=2 ** 40 + 17, obj_offset=2 ** 33, fill='prior_sample')
+    assert np.abs(zo.cpu().numpy() - ref).max() < NORMAL_TOL
+    assert (cs.cpu().numpy() == rcs).mean() > 0.99          # argmin ties in fp32 vs fp64 only
+    if B > 2:   # a shard with the matching object offset reproduces the slice of the global result bit-for-bit
+        lo = B // 2
+        part, _ = a3d_mod.impute(dec, z[lo:], mask[lo:], mu, K=K, seed=2 ** 40 + 17, obj_offset=2 ** 33 + lo)
+        assert torch.equal(part, zo[lo:])
+
+
+def test_sampling_reference_signature(a3d_mod):
+    mu = np.full((2000, 16), 3.0, np.float32)
+    lv = np.full((2000, 16), np.log(4.0), np.float32)
+    s = a3d_mod.sampling(mu, lv, seed=5)
+    assert s.shape == mu.shape and abs(s.mean() - 3.0) < 0.05 and abs(s.std() - 2.0) < 0.05
+    assert np.array_equal(s, a3d_mod.sampling(mu, lv, seed=5))
+    assert not np.array_equal(s, a3d_mod.sampling(mu, lv, seed=6))
+
+
+# ------------------------------------------------------------------------------------------------ scoring
+def test_voxel_precision_recall_exact(a3d_mod):
+    rng = np.random.default_rng(11)
+    B = 6
+    t = (rng.random((B, 64, 64, 64, 1)) < 0.2).astype(np.float32)
+    p = rng.random((B, 64, 64, 64, 1)).astype(np.float32)
+    t[0] = 0; p[1] = 0; t[2] = 1; p[3] = 1
+    p[4].reshape(-1)[:1000] = 0.5                        # exact ties are occupied (>=)
+    tp, fp, fn = a3d_mod.voxelPrecisionRecall(t, p)
+    ref = ar.counts(t, p, 0.5)
+    assert np.array_equal(np.stack([tp, fp, fn], -1).astype(np.int64), ref)
+    tp2, fp2, fn2 = a3d_mod.voxelPrecisionRecall(t, p, prob=0.3)
+    assert np.array_equal(np.stack([tp2, fp2, fn2], -1).astype(np.int64), ar.counts(t, p, 0.3))
+    from a3d import pack_targets
+    d = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=32)
+    assert np.array_equal(pack_targets(d, t).cpu().numpy(), ar.pack_bits(t))
+
+
+# ------------------------------------------------------------------------------------------------ fused anytime path
+def test_anytime_eval_golden(a3d_mod, decoders, golden):
+    dec = decoders[('mn', 'trained')]
+    bits = golden['ev_target_bits']
+    r = a3d_mod.anytime_eval(dec, golden['ev_z'], golden['ev_mask'], golden['ev_mu'], bits, K=2, seed=9,
+                             return_grid=True)
+    assert np.abs(r['z_completed'].cpu().numpy() - golden['ev_zc']).max() < NORMAL_TOL
+    mp = r['mean_prob'].cpu().numpy().reshape(2, -1)
+    assert np.abs(mp[:, golden['sample_idx']] - golden['ev_mean_samples']).max() < PROB_TOL
+    gb = np.unpackbits(golden['ev_mean_bits'], axis=1, bitorder='little').astype(bool)
+    nflip = int(((mp >= 0.5) != gb).sum())
+    assert nflip / gb.size < FLIP_TOL
+    assert np.abs(r['counts'].cpu().numpy() - golden['ev_counts']).sum() <= 2 * nflip + 2
+
+
+@pytest.mark.parametrize('B,K,chunk,fill', [(3, 4, 32, 'prior_sample'), (9, 5, 32, 'normal'), (2, 16, 32, 'mean')])
+def test_anytime_eval_vs_oracle(a3d_mod, weights, B, K, chunk, fill):
+    ws = weights[('mn', 'trained')]
+    dec = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=chunk)      # 9 x 5 decodes -> several chunks
+    dec.set_weights(ws)
+    rng = np.random.default_rng(B + K)
+    z = dr.round_bf16(rng.standard_normal((B, 64)).astype(np.float32))
+    mask = ar.bernoulli_mask(rng, B, 64, 0.5)
+    mu = rng.standard_normal((40, 64)).astype(np.float32)
+    tgt = ar.make_targets(rng, B)
+    r = a3d_mod.anytime_eval(dec, z, mask, mu, tgt, K=K, seed=77, fill=fill, return_grid=True)
+    zc = r['z_completed'].cpu().numpy()
+    ref_mp, ref_cnt = ar.anytime_eval(dr.MODELNET_DECODER, ws, zc, tgt)      # oracle decodes the SAME completed latents
+    mp = r['mean_prob'].cpu().numpy()
+    assert np.abs(mp - ref_mp).max() < PROB_TOL
+    nflip = int(((mp >= 0.5) != (ref_mp >= 0.5)).sum())
+    assert nflip / mp.size < FLIP_TOL
+    cnt = r['counts'].cpu().numpy()
+    assert np.abs(cnt - ref_cnt).sum() <= 2 * nflip
+    # exact invariants of the counts: TP + FN = target occupancy, TP + FP = predicted occupancy
+    assert np.array_equal(cnt[:, 0] + cnt[:, 2], tgt.reshape(B, -1).sum(1).astype(np.int64))
+    assert np.array_equal(cnt[:, 0] + cnt[:, 1], (mp.reshape(B, -1) >= 0.5).sum(1))
+    # counts-only call (no grid) and host-buffer call give the same integers
+    r2 = a3d_mod.anytime_eval(dec, z, mask, mu, ar.pack_bits(tgt), K=K, seed=77, fill=fill)
+    assert torch.equal(r2['counts'], r['counts'])
+    from a3d import anytime_eval_host
+    c3 = anytime_eval_host(dec, z, mask, mu, ar.pack_bits(tgt), K=K, seed=77, fill=fill)
+    assert np.array_equal(c3, cnt)
+
+
+def test_k_copies_of_one_latent_equal_single_decode(a3d_mod, decoders):
+    dec = decoders[('mn', 'trained')]
+    rng = np.random.default_rng(4)
+    z1 = rng.standard_normal((2, 1, 64)).astype(np.float32)
+    tgt = ar.make_targets(rng, 2)
+    a = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=np.repeat(z1, 16, axis=1), return_grid=True)
+    b = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=z1, return_grid=True)
+    assert torch.equal(a['mean_prob'], b['mean_prob']) and torch.equal(a['counts'], b['counts'])
+    single = dec(z1[:, 0])
+    assert np.array_equal(single, b['mean_prob'].cpu().numpy())
+
+
+def test_getEval_reference_return_tuple(a3d_mod, decoders):
+    dec = decoders[('mn', 'trained')]
+    rng = np.random.default_rng(8)
+    B = 4
+    z = rng.standard_normal((B, 64)).astype(np.float32)
+    mu = rng.standard_normal((40, 64)).astype(np.float32)
+    tgt = ar.make_targets(rng, B)
+    cat = np.eye(40, dtype=np.float32)[rng.integers(0, 40, B)]
+    out = a3d_mod.getEval(dec, (z, tgt, cat), mu, missing_prob=0.0)
+    assert len(out) == 10 and out[5:] == (0, 0, 0, 0, 0) and tuple(out[0].shape) == (B, 64, 64, 64, 1)
+    out = a3d_mod.getEval(dec, (z, tgt, cat), mu, missing_prob=0.5, K=4, seed=1, rng=np.random.default_rng(0))
+    assert len(out) == 10 and tuple(out[5].shape) == (B, 64, 64, 64, 1) and 0.0 <= out[7] <= 1.0
+
+
+def test_full_size_properties_config2(a3d_mod, weights):
+    """BASELINE config 2 size (256 objects x K=16 = 4096 decodes): size-independent exact invariants."""
+    ws = weights[('mn', 'default')]
+    dec = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=2048)       # two chunks of 128 objects
+    dec.set_weights(ws)
+    rng = np.random.default_rng(21)
+    B, K = 256, 16
+    z = rng.standard_normal((B, 64)).astype(np.float32)
+    mask = ar.bernoulli_mask(rng, B, 64, 0.5)
+    mu = rng.standard_normal((40, 64)).astype(np.float32)
+    tgt8 = ar.make_targets(rng, 8)
+    bits = np.tile(ar.pack_bits(tgt8), (B // 8, 1))
+    r = a3d_mod.anytime_eval(dec, z, mask, mu, bits, K=K, seed=5)
+    cnt = r['counts'].cpu().numpy()
+    occ = np.tile(tgt8.reshape(8, -1).sum(1).astype(np.int64), B // 8)
+    assert np.array_equal(cnt[:, 0] + cnt[:, 2], occ)                  # TP + FN = target occupancy, exactly
+    assert (cnt >= 0).all() and (cnt.sum(1) <= 262144).all()
+    # idempotence / determinism and shard invariance (objects 100..163 alone, with their global ids)
+    r2 = a3d_mod.anytime_eval(dec, z, mask, mu, bits, K=K, seed=5)
+    assert torch.equal(r2['counts'], r['counts'])
+    r3 = a3d_mod.anytime_eval(dec, z[100:164], mask[100:164], mu, bits[100:164], K=K, seed=5, obj_offset=100)
+    assert torch.equal(r3['counts'], r['counts'][100:164])
+    # spot-check 2 objects of the big batch against the oracle
+    zc = r['z_completed'][[3, 200]].cpu().numpy()
+    tg = np.unpackbits(bits[[3, 200]], axis=1, bitorder='little').reshape(2, 64, 64, 64, 1)
+    _, ref_cnt = ar.anytime_eval(dr.MODELNET_DECODER, ws, zc, tg)
+    assert np.abs(cnt[[3, 200]] - ref_cnt).sum() <= 2 * FLIP_TOL * 262144 * 2
