@@ -252,7 +252,9 @@ def test_k_copies_of_one_latent_equal_single_decode(a3d_mod, decoders):
     tgt = ar.make_targets(rng, 2)
     a = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=np.repeat(z1, 16, axis=1), return_grid=True)
     b = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=z1, return_grid=True)
-    assert torch.equal(a['mean_prob'], b['mean_prob']) and torch.equal(a['counts'], b['counts'])
+    # the K-mean of 16 identical grids equals the single grid up to fp32 summation rounding
+    assert (a['mean_prob'] - b['mean_prob']).abs().max().item() < 1e-6
+    assert (a['counts'] - b['counts']).abs().sum().item() <= 4
     single = dec(z1[:, 0])
     assert np.array_equal(single, b['mean_prob'].cpu().numpy())
 
