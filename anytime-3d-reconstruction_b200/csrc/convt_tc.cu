@@ -19,6 +19,7 @@
 // epilogue of unit i overlaps the main loop of unit i + 1.  Persistent CTAs, static round-robin unit schedule.
 #include <cstdlib>
 
+#include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -41,42 +42,14 @@ struct Cfg {
   static constexpr int BSLOTS = BROWS / BSLOT_ROWS;       // weight slots per input row
   static constexpr int B_BYTES = BSLOT_ROWS * 128;
   static constexpr int A_STAGES = 3;
-  static constexpr int B_STAGES = 4;
+  static constexpr int B_STAGES = (COUT == 256) ? 3 : 4;
+  static constexpr int OUT_STAGE_BYTES = 8 * 4096;         // 32 rows x 128 B per epilogue warp
   static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + NUM_BARS * 8 +
-                                    16 + 2 * NACC * 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + OUT_STAGE_BYTES +
+                                    NUM_BARS * 8 + 16 + 2 * NACC * 4;
   static_assert(BROWS % BSLOT_ROWS == 0, "weight rows per input row must fill whole slots");
   static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
 };
-
-// ELU(alpha = 1) without the slow expm1f: ex2.approx for v <= -1/8 (|rel err| ~ 2e-6), degree-5 Taylor of expm1 for
-// -1/8 < v < 0 (truncation error < 6e-9); branch-free.
-template <int ACT>
-__device__ __forceinline__ float activate(float v) {
-  if constexpr (ACT == A3D_ACT_ELU) {
-    const float e = __expf(v) - 1.f;
-    const float p = v * fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
-    const float neg = v > -0.125f ? p : e;
-    return v > 0.f ? v : neg;
-  } else if constexpr (ACT == A3D_ACT_RELU) {
-    return fmaxf(v, 0.f);
-  } else if constexpr (ACT == A3D_ACT_LRELU) {
-    return v > 0.f ? v : 0.3f * v;
-  } else {
-    return v;
-  }
-}
-
-template <int FMT>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (FMT == A3D_DTYPE_F16) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  } else {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-}
 
 constexpr int kEpiWarps = 8;                 // 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
 constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -92,7 +65,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::A_STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::B_STAGES * C::B_BYTES);
+  uint8_t* smem_o = smem_b + C::B_STAGES * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + C::OUT_STAGE_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::A_STAGES;
   uint64_t* b_full = a_empty + C::A_STAGES;
@@ -167,8 +141,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer: the whole warp stays converged (so descriptors and
+    // addresses live in uniform registers); only tcgen05.mma / commit are predicated on one elected lane
+    {
       uint32_t a_it = 0, b_it = 0, unit_it = 0;
       constexpr uint32_t idesc_full = ptx::make_idesc_f16(128, NACC > 256 ? 256 : NACC, FMT);
       constexpr uint32_t idesc_half = ptx::make_idesc_f16(128, COUT, FMT);
@@ -203,13 +178,14 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                 ptx::tc_fence_after();
                 const uint32_t b_lo = b_lo0 + bs * (C::B_BYTES >> 4);
                 constexpr uint32_t W1 = (NT * 128) >> 4;       // one position along w, in 16-byte units
+                if (ptx::elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                   const uint32_t ko = kk * 2;  // 16 elements * 2 bytes inside the 128-byte swizzled row, >> 4
                   if constexpr (C::PWB && C::BSLOTS == 1) {
                     // COUT = 64: [0,128) = (pw0,tw1 | pw1,tw2) dw=0; [128,192) = pw0,tw3 dw=-1; [192,256) = pw1,tw0 dw=+1
-                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
-                    accum = 1;
+                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                     (kk == 0) ? accum : 1u);
                     ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ((2 * COUT * 128) >> 4) + ko),
                                      idesc_half, 1);
                     ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
@@ -217,8 +193,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                   } else if constexpr (C::PWB) {
                     // COUT = 128: slot 0 = (pw0,tw1 | pw1,tw2) dw=0 (N = 256); slot 1 = pw0,tw3 dw=-1 | pw1,tw0 dw=+1
                     if (j == 0) {
-                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
-                      accum = 1;
+                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                       (kk == 0) ? accum : 1u);
                     } else {
                       ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ko), idesc_half, 1);
                       ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
@@ -227,19 +203,23 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                   } else {
                     // COUT = 256, one pw per unit: slot 0 = dw=0 tap, slot 1 = dw=+-1 tap
                     const uint32_t a_off = (j == 0) ? W1 : (pw ? 2 * W1 : 0);
-                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + a_off + ko), ptx::sw128_desc(b_lo + ko), idesc_full, accum);
-                    accum = 1;
+                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + a_off + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                     (kk == 0) ? accum : 1u);
                   }
                 }
                 ptx::umma_commit<1>(&b_empty[bs]);  // slot reusable once these MMAs retire
+                if (j == C::BSLOTS - 1) ptx::umma_commit<1>(&a_empty[as]);
+                }
+                __syncwarp();
+                if (j == 0) accum = 1;
                 ++b_it;
               }
-              ptx::umma_commit<1>(&a_empty[as]);
               ++a_it;
             }
           }
         }
-        ptx::umma_commit<1>(&t_full[buf]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit<1>(&t_full[buf]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -249,10 +229,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     const int chalf = e >> 2;                          // which half of the accumulator columns
     const int row = quarter * 32 + lane;               // TMEM lane == GEMM row
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int w = row / NT;
-    const int nloc = row % NT;
     constexpr int OD = 2 * WIN;
     constexpr int NCOLS = NACC / 2;                    // columns per warp
+    (void)row;
     uint32_t unit_it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
       const int par = u % C::NPAR;
@@ -261,41 +240,61 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       const int pd = C::PWB ? (par >> 1) : (par >> 2);
       const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
       const int buf = unit_it & 1;
-      const int n = nb * NT + nloc;
       ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * NACC + chalf * NCOLS;
+      uint8_t* stage = smem_o + e * 4096;               // this warp's 32 rows x 128 B staging tile
 #pragma unroll 1
-      for (int g = 0; g < NCOLS / 32; ++g) {
-        uint32_t v[32];
-        ptx::tmem_ld16(tacc + g * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        ptx::tmem_ld16(tacc + g * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        ptx::tmem_ld_wait();
-        const int col = chalf * NCOLS + g * 32;
-        const int pw = C::PWB ? (col / COUT) : (par & 1);
-        const int co = col % COUT;
-        uint32_t o[16];
-        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col);
-        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col);
+      for (int ch = 0; ch < NCOLS / 64; ++ch) {         // 64 output channels (128 B per row) at a time
+        const int col0 = chalf * NCOLS + ch * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 sc = sc4[i], sh = sh4[i];
-          float x0 = fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x);
-          float x1 = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
-          float x2 = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
-          float x3 = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
-          if (!(dbg & 2)) { x0 = activate<ACT>(x0); x1 = activate<ACT>(x1); x2 = activate<ACT>(x2); x3 = activate<ACT>(x3); }
-          o[2 * i] = pack2<FMT>(x0, x1);
-          o[2 * i + 1] = pack2<FMT>(x2, x3);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          ptx::tmem_ld16(tacc + ch * 64 + half * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          ptx::tmem_ld16(tacc + ch * 64 + half * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          ptx::tmem_ld_wait();
+          const int col = col0 + half * 32;
+          uint32_t o[16];
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + col);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = sc4[i], sh = sh4[i];
+            float x0 = fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x);
+            float x1 = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
+            float x2 = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
+            float x3 = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
+            if (!(dbg & 2)) { x0 = activate<ACT>(x0); x1 = activate<ACT>(x1); x2 = activate<ACT>(x2); x3 = activate<ACT>(x3); }
+            o[2 * i] = pack2<FMT>(x0, x1);
+            o[2 * i + 1] = pack2<FMT>(x2, x3);
+          }
+          // lane = row: 4 x 16 B into the row's 128-byte line, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int chunk = (half * 4 + c4) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) =
+                make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          }
         }
-        if (n < n_alloc && !(dbg & 1)) {
-          const size_t vox = (((size_t)n * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * w + pw);
-          uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + co);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-          dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        __syncwarp();
+        // 8 lanes per row: every warp-level store writes four complete 128-byte lines
+        const int pw = C::PWB ? (col0 / COUT) : (par & 1);
+        const int co = col0 % COUT;
+        if (!(dbg & 1)) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const int c16 = lane & 7;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c16 ^ (r & 7)) * 16));
+            const int grow = quarter * 32 + r;
+            const int wr = grow / NT, nr = nb * NT + grow % NT;
+            if (nr < n_alloc) {
+              const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
+              *reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8) = val;
+            }
+          }
         }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&t_empty[buf]);

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -97,6 +98,8 @@ struct a3d_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
   int sticky = 0;
+  bool l4_generic = true;    // A3D_L4_IMPL=ws selects the 2-CTA weight-stationary kernel for the 128->64 layer
+                             // (parity-identical; currently ~8 % slower than the generic 1-CTA kernel)
 };
 
 namespace {
@@ -183,6 +186,32 @@ void pack_tc_weights(const std::vector<float>& wk, int cin, int cout, int fmt, s
   }
 }
 
+// Weight-stationary 2-CTA layout of the 128->64 layer (convt_l4_ws.cu): [class q = pd*2+ph][rank][sd][sh][chunk][128 rows]
+void pack_ws_weights(const std::vector<float>& wk, int cin, int cout, int fmt, std::vector<uint16_t>& out) {
+  const int chunks = cin / 64;
+  out.resize((size_t)4 * 2 * 4 * chunks * 128 * 64);
+  size_t row = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int pd = q >> 1, ph = q & 1;
+    for (int rank = 0; rank < 2; ++rank)
+      for (int sd = 0; sd < 2; ++sd)
+        for (int sh = 0; sh < 2; ++sh) {
+          const int td = tap_of(pd, sd), th = tap_of(ph, sh);
+          for (int c = 0; c < chunks; ++c)
+            for (int r = 0; r < 128; ++r, ++row) {
+              int tw, co;
+              if (r < 64) { tw = rank == 0 ? 1 : 2; co = r; }            // dw = 0: rank 0 = pw0, rank 1 = pw1
+              else if (r < 96) { tw = 3; co = 32 * rank + (r - 64); }     // dw = -1 (pw0), N-half of this rank
+              else { tw = 0; co = 32 * rank + (r - 96); }                 // dw = +1 (pw1), N-half of this rank
+              const size_t tap = ((size_t)td * 4 + th) * 4 + tw;
+              const float* src = &wk[(tap * cout + co) * cin + (size_t)c * 64];
+              uint16_t* dst = &out[row * 64];
+              for (int i = 0; i < 64; ++i) dst[i] = cvt16(src[i], fmt);
+            }
+        }
+  }
+}
+
 void pack_tco_weights(const std::vector<float>& wk, int ntap, int cin, int cout, int fmt, std::vector<uint16_t>& out) {
   out.resize((size_t)ntap * cin * cout);
   for (int t = 0; t < ntap; ++t)
@@ -255,6 +284,19 @@ int finalize_weights(a3d_handle* h) {
     if ((rc = upload(sc.data(), sc.size() * 4, (void**)&L.scale))) return rc;
     if ((rc = upload(sf.data(), sf.size() * 4, (void**)&L.shift))) return rc;
     if ((rc = make_tmaps(h, li))) return rc;
+    if (li == 2) {
+      pack_ws_weights(h->w[base], L.cin, L.cout, fmt, p16);
+      if ((rc = upload(p16.data(), p16.size() * 2, &L.wgt_ws))) return rc;
+      EncodeTiledFn enc = get_encode_fn();
+      const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      cuuint64_t dims[2] = {64, (cuuint64_t)(p16.size() / 64)};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, 256};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&L.tmap_wgt_ws, dt, 2, L.wgt_ws, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(ws weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    }
   }
   // final kernel [4,4,4,1,64] is already [tap][ci]
   if ((rc = upload(h->w[26].data(), h->w[26].size() * 4, (void**)&h->d_w5))) return rc;
@@ -300,6 +342,9 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
   for (int li = 0; li < 3; ++li) {
     if (h->desc.impl == A3D_IMPL_SIMT)
       rc = launch_convt_s2_simt(h->conv[li], h->act[li + 1], h->act[li + 2], n, fmt, act, st, &h->launches);
+    else if (li == 2 && !h->l4_generic)
+      rc = launch_convt_l4_ws(h->conv[li].tmap_act, h->conv[li].tmap_wgt_ws, h->act[li + 2], h->conv[li].scale,
+                              h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
     else
       rc = launch_convt_s2_tc(h->conv[li], h->act[li + 2], n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
     if (rc) return rc;
@@ -377,6 +422,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   h->dense_units = h->grid0 * h->grid0 * h->grid0 * h->ch0;  // :120
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
+  { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = !(e && std::string(e) == "ws"); }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
   h->act_elems[0] = 512; h->act_elems[1] = 64 * 512; h->act_elems[2] = 512 * 256; h->act_elems[3] = 4096 * 128;
@@ -404,7 +450,7 @@ void a3d_destroy(a3d_handle* h) {
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
   cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16);
-  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
+  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -29,6 +29,8 @@ struct ConvLayer {
   CUtensorMap tmap_act;   // 5-D view (c, n, w, h, d) of the input activations, box (64, 128/W, W+2, 1, 1), SW128
   CUtensorMap tmap_wgt;   // 2-D view (64 ci, rows) of the per-(parity,tap,chunk) repacked weights, box (64, 256), SW128
   void* wgt_packed = nullptr;   // device, 16-bit
+  CUtensorMap tmap_wgt_ws;      // weight-stationary 2-CTA layout (128->64 layer only)
+  void* wgt_ws = nullptr;
   // SIMT path: [tap 64][ci][co] 16-bit
   void* wgt_tco = nullptr;
   float* scale = nullptr;  // folded BN: y = scale*conv + shift
@@ -40,6 +42,9 @@ int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const flo
                     const float* h0, void* a0, const void* w1_tco, const float* s1, const float* h1, void* a1,
                     int fmt, int act, cudaStream_t st, int64_t* launches);
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
+                       cudaStream_t st, int64_t* launches);
+int launch_convt_l4_ws(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
+                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
 int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t n, int fmt, int act,
                          cudaStream_t st, int64_t* launches);

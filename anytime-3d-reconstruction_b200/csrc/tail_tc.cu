@@ -98,8 +98,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp converged, issue predicated on an elected lane)
+    {
       constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, FMT);
       ptx::mbar_wait(w_full, 0);
       const uint32_t w_lo = ptx::sw128_desc_lo(ptx::smem_u32(smem_w));
@@ -112,6 +112,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           ptx::mbar_wait(&a_full[s], (it >> 1) & 1);
           ptx::tc_fence_after();
           const uint32_t a_lo = a_lo0 + s * (kABytes >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
 #pragma unroll
@@ -122,6 +123,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           }
           ptx::umma_commit<1>(&a_empty[s]);
           ptx::umma_commit<1>(&t_full[s]);
+          }
+          __syncwarp();
         }
       }
     }

@@ -14,6 +14,12 @@ rng = np.random.default_rng(0)
 zc = torch.from_numpy(rng.standard_normal((B, K, 64)).astype(np.float32)).cuda()
 bits = torch.zeros((B, 32768), dtype=torch.uint8, device='cuda')
 dec.set_profiling(True)
+rec = []
 for i in range(reps):
     a3d.anytime_eval(dec, None, None, None, bits, z_completed=zc)
-    print(os.environ.get('A3D_DEBUG_FLAGS', '0'), {k: round(v, 3) for k, v in dec.stage_times_ms().items()}, flush=True)
+    rec.append(dec.stage_times_ms())
+    if i == reps - 1 or reps <= 3:
+        print(os.environ.get('A3D_DEBUG_FLAGS', '0'), {k: round(v, 3) for k, v in rec[-1].items()}, flush=True)
+if reps > 3:
+    med = {k: round(float(np.median([r[k] for r in rec[1:]])), 3) for k in rec[0]}
+    print('median', med, 'total', round(sum(med.values()), 2), flush=True)
