@@ -301,22 +301,34 @@ int finalize_weights(a3d_handle* h) {
   // final kernel [4,4,4,1,64] is already [tap][ci]
   if ((rc = upload(h->w[26].data(), h->w[26].size() * 4, (void**)&h->d_w5))) return rc;
   {
-    p16.resize(h->w[26].size());
-    for (size_t i = 0; i < p16.size(); ++i) p16[i] = cvt16(h->w[26][i], fmt);
+    // B operand of the tail GEMM: rows n = (td*4 + th)*2 + pw of  Wa (delta_w = 0, tap_w = pw + 1),
+    // Wb0 (delta_w = -1: tap_w 3 in the pw = 0 rows, zeros in pw = 1), Wb1 (delta_w = +1: tap_w 0 in the pw = 1 rows)
+    p16.assign((size_t)96 * 64, cvt16(0.f, fmt));
+    for (int td = 0; td < 4; ++td)
+      for (int th = 0; th < 4; ++th)
+        for (int pw = 0; pw < 2; ++pw) {
+          const int n = (td * 4 + th) * 2 + pw;
+          const float* wa = &h->w[26][(size_t)((td * 4 + th) * 4 + (pw + 1)) * 64];
+          const float* wb = &h->w[26][(size_t)((td * 4 + th) * 4 + (pw ? 0 : 3)) * 64];
+          for (int ci = 0; ci < 64; ++ci) {
+            p16[(size_t)n * 64 + ci] = cvt16(wa[ci], fmt);
+            p16[(size_t)((pw ? 64 : 32) + n) * 64 + ci] = cvt16(wb[ci], fmt);
+          }
+        }
     if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_16))) return rc;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return A3D_ERR_CUDA; }
     const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    cuuint64_t dims[5] = {64, 32, 32, 32, (cuuint64_t)h->max_chunk};   // (c, w, h, d, n)
-    cuuint64_t strides[4] = {128, 128 * 32, 128 * 32 * 32, 128ull * 32 * 32 * 32};
+    cuuint64_t dims[5] = {64, 32, 32, 32, (cuuint64_t)h->max_chunk};   // (c, h, d, w, n): GEMM rows come out w-slowest
+    cuuint64_t strides[4] = {128 * 32, 128 * 32 * 32, 128, 128ull * 32 * 32 * 32};
     cuuint32_t box[5] = {64, 8, 8, 8, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&h->tmap_a4, dt, 5, h->act[4], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
-    cuuint64_t wd[2] = {64, 64};
+    cuuint64_t wd[2] = {64, 96};
     cuuint64_t ws[1] = {128};
-    cuuint32_t wb[2] = {64, 64};
+    cuuint32_t wb[2] = {64, 96};
     r = enc(&h->tmap_w5, dt, 2, h->d_w5_16, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }

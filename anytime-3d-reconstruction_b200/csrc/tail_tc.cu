@@ -3,10 +3,14 @@
 //   mean over the K post-sigmoid grids of an object                                 nolbo_test.py:167-177
 //   yPred = (mean >= thr), TP / FP / FN against the bit-packed target               function.py:100-115
 //
-// Cout = 1 makes the gather form GEMV-like, so the layer is run in SCATTER form instead: a dense tap GEMM
-//     Y[j, t] = sum_ci X[j, ci] * W5[t, ci]          (M = input voxels, N = 64 taps, K = 64 channels)
-// on the tensor cores, followed by col2im  out[2j + t - 1] += Y[j, t]  done separably on the accumulators:
-//   w axis: warp shuffles (a warp holds 4 rows of 8 consecutive w),  h and d axes: two shared-memory exchanges.
+// Cout = 1 makes the full gather form GEMV-like, so the layer is split per axis:
+//   w axis  -- gathered inside the GEMM:  Zw[j, (td, th, pw)] = X[j]*Wa + X[j - e_w]*Wb0 + X[j + e_w]*Wb1
+//              (M = input voxels, N = 32 = 4 x 4 taps of (d, h) x 2 output parities of w, K = 64 channels; Wb0 / Wb1 hold
+//              the delta_w = -1 / +1 taps in the pw = 0 / pw = 1 columns and zeros elsewhere).  GEMM rows are ordered
+//              (w, d, h) with w slowest, so a shift of +-1 in w is a shift of 64 rows = 8 KB = whole swizzle atoms and is
+//              just another start address of the A descriptor over the same TMA-loaded tile.
+//   h axis  -- col2im on the accumulators with warp shuffles (a warp holds 4 d-rows of 8 consecutive h).
+//   d axis  -- col2im through one shared-memory exchange.
 // One CTA owns an 8x8x8 block of input voxels (origin -1 + 7*i per axis, TMA zero-fills the halo) = 14^3 complete
 // output voxels, loops over the K samples of the object with double-buffered TMA stages / TMEM accumulators, keeps the
 // running sum of sigmoids in registers and finally thresholds, compares with the target bits and reduces the counts.
@@ -23,15 +27,17 @@ constexpr int kBlk = 8;                         // input voxels per axis per CTA
 constexpr int kPos = kBlk * kBlk * kBlk;        // 512 GEMM rows = 4 M-tiles of 128
 constexpr int kBlocksAxis = 5;                  // origins -1, 6, 13, 20, 27 cover outputs 0..63
 constexpr int kItemsPerObj = kBlocksAxis * kBlocksAxis * kBlocksAxis;
-constexpr int kABytes = kPos * 128;             // 64 KB per stage
-constexpr int kWBytes = 64 * 128;               // W5 as the B operand: 64 taps x 64 ci
-constexpr int kExH = 16 * kPos * 4;             // h-exchange: 16 values per voxel
-constexpr int kExD = 8 * kPos * 4;              // d-exchange: 8 values per voxel
+constexpr int kABytes = kPos * 128;             // 64 KB tile per stage
+constexpr int kPad = 64 * 128;                  // 8 KB of zeros before / between / after the tiles (w-shifted views)
+constexpr int kAStride = kABytes + kPad;
+constexpr int kWRows = 96;                      // Wa | Wb0 | Wb1, 32 rows each
+constexpr int kWBytes = kWRows * 128;
+constexpr int kExD = 8 * kPos * 4;              // d-exchange: 8 values per voxel (double buffered)
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // 640
-constexpr int kSmem = 1024 + 2 * kABytes + kWBytes + kExH + kExD + 16 * 8 + 16;
+constexpr int kSmem = 1024 + kPad + 2 * kAStride + kWBytes + 2 * kExD + 16 * 8 + 16;
 
-__device__ __forceinline__ void epi_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * kEpiWarps) : "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory"); }
 
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -40,11 +46,10 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
                unsigned long long* __restrict__ counts, float* __restrict__ mean_prob) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_w = smem + 2 * kABytes;
-  float* exH = reinterpret_cast<float*>(smem_w + kWBytes);
-  float* exD = exH + 16 * kPos;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(exD + 8 * kPos);
+  uint8_t* smem_a = smem + kPad;                 // tile s at smem_a + s * kAStride, zero pads around
+  uint8_t* smem_w = smem + kPad + 2 * kAStride;
+  float* exD = reinterpret_cast<float*>(smem_w + kWBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(exD + 2 * 8 * kPos);
   uint64_t* a_full = bars;          // [2]
   uint64_t* a_empty = bars + 2;     // [2]
   uint64_t* t_full = bars + 4;      // [2]
@@ -71,9 +76,15 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<1>(tmem_slot, 512);
+    ptx::tmem_alloc<1>(tmem_slot, 256);
     ptx::tmem_relinquish<1>();
   }
+  // zero the three pads: rows read by the w-shifted A views at the block faces must contribute exactly 0
+  for (int i = threadIdx.x; i < 3 * (kPad / 16); i += blockDim.x) {
+    const int p = i / (kPad / 16), o = i % (kPad / 16);
+    *reinterpret_cast<uint4*>(smem + p * kAStride + o * 16) = make_uint4(0, 0, 0, 0);
+  }
+  ptx::fence_proxy_async();         // generic-proxy zeros visible to the tensor-core (async proxy) reads
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -93,17 +104,19 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           const int s = it & 1;
           ptx::mbar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
           ptx::mbar_expect_tx(&a_full[s], kABytes);
-          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, aw, ah, ad, (int)(b * K + k));
+          // tensor-map dims are (c, h, d, w, n): rows land as (w, d, h) with h fastest
+          ptx::tma_load_5d(smem_a + s * kAStride, &tmap_a4, &a_full[s], 0, ah, ad, aw, (int)(b * K + k));
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (warp converged, issue predicated on an elected lane)
     {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, FMT);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(128, 32, FMT);
       ptx::mbar_wait(w_full, 0);
       const uint32_t w_lo = ptx::sw128_desc_lo(ptx::smem_u32(smem_w));
       const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
+      constexpr uint32_t WSH = kPad >> 4;        // one step along w = 64 rows
       uint32_t it = 0;
       for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
         for (int k = 0; k < K; ++k, ++it) {
@@ -111,32 +124,38 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           ptx::mbar_wait(&t_empty[s], ((it >> 1) & 1) ^ 1);
           ptx::mbar_wait(&a_full[s], (it >> 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t a_lo = a_lo0 + s * (kABytes >> 4);
+          const uint32_t a_lo = a_lo0 + s * (kAStride >> 4);
           if (ptx::elect_one()) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 4; ++m) {
+              const uint32_t tacc = tmem_base + s * 128 + m * 32;
+              const uint32_t am = a_lo + m * (16384 >> 4);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              ptx::umma_f16<1>(tmem_base + s * 256 + m * 64, ptx::sw128_desc(a_lo + m * (16384 >> 4) + kk * 2),
-                               ptx::sw128_desc(w_lo + kk * 2), idesc, kk > 0);
+              for (int kk = 0; kk < 4; ++kk) {
+                ptx::umma_f16<1>(tacc, ptx::sw128_desc(am + kk * 2), ptx::sw128_desc(w_lo + kk * 2), idesc, kk > 0);
+                ptx::umma_f16<1>(tacc, ptx::sw128_desc(am - WSH + kk * 2),
+                                 ptx::sw128_desc(w_lo + ((32 * 128) >> 4) + kk * 2), idesc, 1);
+                ptx::umma_f16<1>(tacc, ptx::sw128_desc(am + WSH + kk * 2),
+                                 ptx::sw128_desc(w_lo + ((64 * 128) >> 4) + kk * 2), idesc, 1);
+              }
             }
-          }
-          ptx::umma_commit<1>(&a_empty[s]);
-          ptx::umma_commit<1>(&t_full[s]);
+            ptx::umma_commit<1>(&a_empty[s]);
+            ptx::umma_commit<1>(&t_full[s]);
           }
           __syncwarp();
         }
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue: col2im + sigmoid + K-mean + threshold + counts
+    // ===================================================== epilogue: col2im (h, d) + sigmoid + K-mean + threshold + counts
     const int e = warp - 4;
-    const int m = e >> 2;                      // M-tile (two d-slices of the block)
+    const int m = e >> 2;                      // M-tile (two w-slices of the block)
     const int quarter = e & 3;                 // TMEM lane quarter == warp % 4
-    const int r = m * 128 + quarter * 32 + lane;   // voxel index in the block: (ld*8 + lh)*8 + lw
-    const int ld = r >> 6, lh = (r >> 3) & 7, lw = r & 7;
+    const int r = m * 128 + quarter * 32 + lane;   // voxel index in the block: (lw*8 + ld)*8 + lh
+    const int lw = r >> 6, ld = (r >> 3) & 7, lh = r & 7;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float invk = 1.f / (float)K;
+    const int rm = (r - 8) & (kPos - 1), rp = (r + 8) & (kPos - 1);   // d - 1 / d + 1 neighbours
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int64_t b = item / kItemsPerObj;
@@ -149,58 +168,40 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
         const int s = it & 1;
         ptx::mbar_wait(&t_full[s], (it >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t tacc = tmem_base + lane_base + s * 256 + m * 64;
-        // ---- w axis: out_w[pw=0][j] = Y_j[tw=1] + Y_{j-1}[tw=3];  out_w[pw=1][j] = Y_j[tw=2] + Y_{j+1}[tw=0]
-        float zw[4][4][2];  // [td][th][pw]
-#pragma unroll
-        for (int td = 0; td < 4; ++td) {
-          uint32_t y[16];   // [th][tw]
-          ptx::tmem_ld16(tacc + td * 16, y);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int th = 0; th < 4; ++th) {
-            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(y[th * 4 + 3]), 1);
-            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(y[th * 4 + 0]), 1);
-            zw[td][th][0] = __uint_as_float(y[th * 4 + 1]) + up;
-            zw[td][th][1] = __uint_as_float(y[th * 4 + 2]) + dn;
-          }
-        }
+        const uint32_t tacc = tmem_base + lane_base + s * 128 + m * 32;
+        uint32_t y[32];   // [td][th][pw]
+        ptx::tmem_ld16(tacc, *reinterpret_cast<uint32_t(*)[16]>(&y[0]));
+        ptx::tmem_ld16(tacc + 16, *reinterpret_cast<uint32_t(*)[16]>(&y[16]));
+        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&t_empty[s]);   // accumulator is in registers: release the TMEM buffer
-        // ---- h axis through shared memory
-#pragma unroll
-        for (int td = 0; td < 4; ++td)
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            exH[((td * 2 + 0) * 2 + pw) * kPos + r] = zw[td][3][pw];
-            exH[((td * 2 + 1) * 2 + pw) * kPos + r] = zw[td][0][pw];
-          }
-        epi_sync(1);
+        // ---- h axis (lanes are 8 consecutive h): out_h[ph=0][j] = Z_j[th=1] + Z_{j-1}[th=3]; [ph=1] = Z_j[th=2] + Z_{j+1}[th=0]
         float zh[4][2][2];  // [td][ph][pw]
-        const int rm = (r - 8) & (kPos - 1), rp = (r + 8) & (kPos - 1);
 #pragma unroll
         for (int td = 0; td < 4; ++td)
 #pragma unroll
           for (int pw = 0; pw < 2; ++pw) {
-            zh[td][0][pw] = zw[td][1][pw] + exH[((td * 2 + 0) * 2 + pw) * kPos + rm];
-            zh[td][1][pw] = zw[td][2][pw] + exH[((td * 2 + 1) * 2 + pw) * kPos + rp];
+            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(y[(td * 4 + 3) * 2 + pw]), 1);
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(y[(td * 4 + 0) * 2 + pw]), 1);
+            zh[td][0][pw] = __uint_as_float(y[(td * 4 + 1) * 2 + pw]) + up;
+            zh[td][1][pw] = __uint_as_float(y[(td * 4 + 2) * 2 + pw]) + dn;
           }
-        // ---- d axis through shared memory
+        // ---- d axis through shared memory (double buffered across samples: one block sync per sample)
+        float* ex = exD + (it & 1) * (8 * kPos);
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
           for (int pw = 0; pw < 2; ++pw) {
-            exD[((0 * 2 + ph) * 2 + pw) * kPos + r] = zh[3][ph][pw];
-            exD[((1 * 2 + ph) * 2 + pw) * kPos + r] = zh[0][ph][pw];
+            ex[((0 * 2 + ph) * 2 + pw) * kPos + r] = zh[3][ph][pw];
+            ex[((1 * 2 + ph) * 2 + pw) * kPos + r] = zh[0][ph][pw];
           }
-        epi_sync(2);
-        const int dm = (r - 64) & (kPos - 1), dp = (r + 64) & (kPos - 1);
+        epi_sync();
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
           for (int pw = 0; pw < 2; ++pw) {
-            const float o0 = zh[1][ph][pw] + exD[((0 * 2 + ph) * 2 + pw) * kPos + dm];
-            const float o1 = zh[2][ph][pw] + exD[((1 * 2 + ph) * 2 + pw) * kPos + dp];
+            const float o0 = zh[1][ph][pw] + ex[((0 * 2 + ph) * 2 + pw) * kPos + rm];
+            const float o1 = zh[2][ph][pw] + ex[((1 * 2 + ph) * 2 + pw) * kPos + rp];
             psum[(0 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o0)) : o0;
             psum[(1 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o1)) : o1;
           }
@@ -243,7 +244,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 256);
 }
 
 }  // namespace
