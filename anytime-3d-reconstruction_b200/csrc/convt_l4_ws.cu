@@ -45,7 +45,9 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                    uint16_t* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
                    int n_blocks, int n_alloc) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128-byte swizzle, computed on the shared-window address so the pointer keeps its
+  // __shared__ provenance (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + W_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + A_STAGES * A_BYTES);

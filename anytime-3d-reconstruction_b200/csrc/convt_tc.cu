@@ -62,7 +62,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   constexpr int CIN = C::CIN, COUT = C::COUT, WIN = C::WIN, NT = C::NT, NACC = C::NACC;
   (void)CIN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128-byte swizzle, computed on the shared-window address so the pointer keeps its
+  // __shared__ provenance (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::A_STAGES * C::A_BYTES;
   uint8_t* smem_o = smem_b + C::B_STAGES * C::B_BYTES;

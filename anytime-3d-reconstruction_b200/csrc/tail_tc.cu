@@ -45,7 +45,9 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
                int K, int final_sigmoid, const uint8_t* __restrict__ target_bits, float thr,
                unsigned long long* __restrict__ counts, float* __restrict__ mean_prob) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128-byte swizzle, computed on the shared-window address so the pointer keeps its
+  // __shared__ provenance (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem + kPad;                 // tile s at smem_a + s * kAStride, zero pads around
   uint8_t* smem_w = smem + kPad + 2 * kAStride;
   float* exD = reinterpret_cast<float*>(smem_w + kWBytes);

@@ -38,6 +38,8 @@ D = 64
 NCAT = 40
 L4_MACS = 1_952_382_976          # exact MACs of the 128->64 layer per decode
 FLOP_PER_DECODE = 6.663830528e9
+WORKLOAD = (f'ModelNet VAE_dr anytime decode: {len(RATES)} missing rates (25/50/75%) x {B_PER_RATE} objects x K={K} '
+            f'prior samples per GPU per step, D={D}, Keras-default random-init weights, synthetic ellipsoid targets')
 
 
 def parse():
@@ -160,8 +162,8 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'anytime voxel reconstructions/sec', 'value': val, 'unit': 'objects/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'ModelNet VAE_dr anytime decode, K={K} prior samples, D={D}; bounded sample of '
-                               f'{n_obj} objects ({n_obj * K} decodes) per step on the host CPU'},
+        'config': {'workload': WORKLOAD, 'reference_sample': f'bounded sample of {n_obj} objects ({n_obj * K} decodes) '
+                                                              f'of that workload per step on the host CPU'},
         'cpu_baseline': {'value': val, 'unit': 'objects/s', 'cores': os.cpu_count(), 'kind': 'port',
                          'sample': f'{n_obj} objects x K={K} per step, torch CPU fp32 oracle (reference needs '
                                    f'TensorFlow, unavailable offline)'},
@@ -294,9 +296,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype + ' operands, f32 accumulate',
             'data': 'synthetic',
-            'config': {'workload': f'ModelNet VAE_dr anytime decode: {len(RATES)} missing rates (25/50/75%) x '
-                                   f'{B_PER_RATE} objects x K={K} prior samples per GPU per step, D={D}, '
-                                   f'Keras-default random-init weights, synthetic ellipsoid targets',
+            'config': {'workload': WORKLOAD,
                        'decodes_per_step_per_gpu': B_PER_RATE * K * len(RATES), 'parallelism': f'objects sharded x{world}',
                        'l2_policy': 'activation working set per step (65 GB/GPU) is streamed through HBM, >> 126 MB L2'},
             'decodes_per_s': value * K,
