@@ -27,8 +27,9 @@ namespace a3d {
 
 namespace {
 
-template <int CIN_, int COUT_, int WIN_>
+template <int CIN_, int COUT_, int WIN_, int TUNE_ = 0>
 struct Cfg {
+  static constexpr int TUNE = TUNE_;
   static constexpr int CIN = CIN_, COUT = COUT_, WIN = WIN_;
   static constexpr int NT = 128 / WIN;                    // decodes per unit
   static constexpr bool PWB = (COUT <= 128);              // both pw parities in one unit
@@ -41,9 +42,10 @@ struct Cfg {
   static constexpr int BSLOT_ROWS = 256;
   static constexpr int BSLOTS = BROWS / BSLOT_ROWS;       // weight slots per input row
   static constexpr int B_BYTES = BSLOT_ROWS * 128;
-  static constexpr int A_STAGES = 3;
-  static constexpr int B_STAGES = (COUT == 256) ? 3 : 4;
-  static constexpr int OUT_STAGE_BYTES = 8 * 4096;         // 32 rows x 128 B per epilogue warp
+  static constexpr bool STAGED_STORES = (TUNE == 0);
+  static constexpr int A_STAGES = (TUNE == 0) ? 3 : (COUT == 64 ? 5 : (COUT == 128 ? 4 : 3));
+  static constexpr int B_STAGES = (TUNE == 0) ? ((COUT == 256) ? 3 : 4) : 4;
+  static constexpr int OUT_STAGE_BYTES = STAGED_STORES ? 8 * 4096 : 0;   // 32 rows x 128 B per epilogue warp
   static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + OUT_STAGE_BYTES +
                                     NUM_BARS * 8 + 16 + 2 * NACC * 4;
@@ -270,6 +272,20 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
           }
+          if constexpr (!C::STAGED_STORES) {
+            // direct: this lane's row, 64 contiguous bytes
+            const int grow = quarter * 32 + lane;
+            const int wr = grow / NT, nr = nb * NT + grow % NT;
+            const int pw_ = C::PWB ? (col / COUT) : (par & 1);
+            if (nr < n_alloc && !(dbg & 1)) {
+              const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw_);
+              uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + (col % COUT));
+              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+              dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+            }
+          } else {
           // lane = row: 4 x 16 B into the row's 128-byte line, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
@@ -277,7 +293,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) =
                 make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
           }
+          }
         }
+        if constexpr (C::STAGED_STORES) {
         __syncwarp();
         // 8 lanes per row: every warp-level store writes four complete 128-byte lines
         const int pw = C::PWB ? (col0 / COUT) : (par & 1);
@@ -297,6 +315,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
         }
         __syncwarp();
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&t_empty[buf]);
@@ -352,12 +371,16 @@ size_t convt_tc_smem_bytes(int cin, int cout, int win) {
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches) {
   int rc;
+  static const int tune = getenv("A3D_CONV_TUNE") ? atoi(getenv("A3D_CONV_TUNE")) : 0;
   if (L.cin == 512 && L.cout == 256 && L.win == 4)
-    rc = launch_cfg<Cfg<512, 256, 4>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = tune ? launch_cfg<Cfg<512, 256, 4, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+              : launch_cfg<Cfg<512, 256, 4, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else if (L.cin == 256 && L.cout == 128 && L.win == 8)
-    rc = launch_cfg<Cfg<256, 128, 8>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = tune ? launch_cfg<Cfg<256, 128, 8, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+              : launch_cfg<Cfg<256, 128, 8, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else if (L.cin == 128 && L.cout == 64 && L.win == 16)
-    rc = launch_cfg<Cfg<128, 64, 16>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = tune ? launch_cfg<Cfg<128, 64, 16, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+              : launch_cfg<Cfg<128, 64, 16, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else {
     set_error("tcgen05 ConvT path supports (512->256,W4), (256->128,W8), (128->64,W16); got %d->%d W%d", L.cin,
               L.cout, L.win);

@@ -75,6 +75,7 @@ struct a3d_handle {
   // device weights
   float *d_wd = nullptr, *d_bd = nullptr, *d_s0 = nullptr, *d_h0 = nullptr;   // dense + folded BN0
   void* d_w1_tco = nullptr; float *d_s1 = nullptr, *d_h1 = nullptr;          // stride-1 layer
+  void* d_mt = nullptr; CUtensorMap tmap_a0, tmap_mt;                         // ... as a dense GEMM (tcgen05 path)
   ConvLayer conv[3];                                                           // stride-2 hidden layers
   float* d_w5 = nullptr;                                                       // final kernel [tap][ci] fp32
   void* d_w5_16 = nullptr;                                                     // same, operand dtype (tcgen05 tail)
@@ -270,6 +271,36 @@ int finalize_weights(a3d_handle* h) {
   fold_bn(h->w[7], h->w[8], h->w[9], h->w[10], sc, sf);
   if ((rc = upload(sc.data(), sc.size() * 4, (void**)&h->d_s1))) return rc;
   if ((rc = upload(sf.data(), sf.size() * 4, (void**)&h->d_h1))) return rc;
+  if (h->desc.impl == A3D_IMPL_TCGEN05) {
+    // dense [512 x 32768] matrix of the stride-1 layer: Mt[(o, co)][(i, ci)] = W[t = o - i + 1][co][ci]
+    const int cout = h->desc.filters[0], cin = h->ch0;
+    p16.assign((size_t)64 * cout * 512, cvt16(0.f, fmt));
+    for (int o = 0; o < 64; ++o)
+      for (int i = 0; i < 64; ++i) {
+        const int td = (o >> 4) - (i >> 4) + 1, th = ((o >> 2) & 3) - ((i >> 2) & 3) + 1, tw = (o & 3) - (i & 3) + 1;
+        if (td < 0 || td > 3 || th < 0 || th > 3 || tw < 0 || tw > 3) continue;
+        const float* src = &h->w[6][(size_t)((td * 4 + th) * 4 + tw) * cout * cin];
+        for (int co = 0; co < cout; ++co)
+          for (int ci = 0; ci < cin; ++ci)
+            p16[((size_t)o * cout + co) * 512 + (size_t)i * cin + ci] = cvt16(src[(size_t)co * cin + ci], fmt);
+      }
+    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_mt))) return rc;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return A3D_ERR_CUDA; }
+    const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    cuuint32_t es[2] = {1, 1};
+    cuuint64_t st1[1] = {1024};
+    cuuint64_t da[2] = {512, (cuuint64_t)h->max_chunk};
+    cuuint32_t ba[2] = {64, 128};
+    CUresult r = enc(&h->tmap_a0, dt, 2, h->act[0], da, st1, ba, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(a0) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    cuuint64_t dm[2] = {512, (cuuint64_t)64 * cout};
+    cuuint32_t bm[2] = {64, 256};
+    r = enc(&h->tmap_mt, dt, 2, h->d_mt, dm, st1, bm, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Mt) failed: %d", (int)r); return A3D_ERR_CUDA; }
+  }
   // stride-2 hidden layers
   for (int li = 0; li < 3; ++li) {
     ConvLayer& L = h->conv[li];
@@ -347,9 +378,15 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
   const int fmt = h->desc.operand_dtype, act = h->desc.activation;
   int rc;
   if (h->profiling) cudaEventRecord(h->ev[0], st);
+  const bool simt_l1 = h->desc.impl == A3D_IMPL_SIMT;
   rc = launch_dense_l1(z_dev, n, h->desc.latent_dim, h->d_wd, h->d_bd, h->d_s0, h->d_h0, h->act[0], h->d_w1_tco,
-                       h->d_s1, h->d_h1, h->act[1], fmt, act, st, &h->launches);
+                       h->d_s1, h->d_h1, h->act[1], fmt, act, simt_l1, st, &h->launches);
   if (rc) return rc;
+  if (!simt_l1) {
+    rc = launch_gemm_l1(h->tmap_a0, h->tmap_mt, h->act[1], h->d_s1, h->d_h1, n, h->max_chunk, fmt, act, h->num_sms, st,
+                        &h->launches);
+    if (rc) return rc;
+  }
   if (h->profiling) cudaEventRecord(h->ev[1], st);
   for (int li = 0; li < 3; ++li) {
     if (h->desc.impl == A3D_IMPL_SIMT)
@@ -461,7 +498,7 @@ void a3d_destroy(a3d_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
-  cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16);
+  cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16);
   for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);

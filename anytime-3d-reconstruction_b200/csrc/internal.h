@@ -40,7 +40,10 @@ struct ConvLayer {
 // kernels (defined in the .cu files); all asynchronous on `st`
 int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const float* bd, const float* s0,
                     const float* h0, void* a0, const void* w1_tco, const float* s1, const float* h1, void* a1,
-                    int fmt, int act, cudaStream_t st, int64_t* launches);
+                    int fmt, int act, bool do_s1, cudaStream_t st, int64_t* launches);
+int launch_gemm_l1(const CUtensorMap& tmap_a0, const CUtensorMap& tmap_mt, void* a1, const float* scale,
+                   const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, cudaStream_t st,
+                   int64_t* launches);
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
 int launch_convt_l4_ws(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,

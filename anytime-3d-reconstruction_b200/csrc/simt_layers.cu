@@ -139,21 +139,21 @@ __global__ void to_f32_kernel(const uint16_t* __restrict__ src, float* __restric
 
 int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const float* bd, const float* s0,
                     const float* h0, void* a0, const void* w1_tco, const float* s1, const float* h1, void* a1,
-                    int fmt, int act, cudaStream_t st, int64_t* launches) {
+                    int fmt, int act, bool do_s1, cudaStream_t st, int64_t* launches) {
   if (n <= 0) return A3D_OK;
   constexpr int NB = 16;
   const int blocks1 = (int)((n + NB - 1) / NB);
   if (fmt == A3D_DTYPE_F16) {
     dense_kernel<A3D_DTYPE_F16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
-    convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+    if (do_s1) convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
                                                                (uint16_t*)a1, n, act);
   } else {
     dense_kernel<A3D_DTYPE_BF16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
-    convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
+    if (do_s1) convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
                                                                 (uint16_t*)a1, n, act);
   }
   A3D_CUDA_OK(cudaGetLastError());
-  if (launches) *launches += 2;
+  if (launches) *launches += do_s1 ? 2 : 1;
   return A3D_OK;
 }
 
