@@ -51,10 +51,10 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + W_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + A_STAGES * A_BYTES);
-  uint64_t* a_full = bars;                    // [A_STAGES]  used on the leader CTA (2 arrivals + both CTAs' bytes)
+  uint64_t* a_full = bars;                    // [A_STAGES]  used on the leader CTA (1 arrival + both CTAs' bytes)
   uint64_t* a_empty = a_full + A_STAGES;      // [A_STAGES]  per CTA, multicast commit
   uint64_t* t_full = a_empty + A_STAGES;      // [NBUF]      per CTA, multicast commit
-  uint64_t* t_empty = t_full + NBUF;          // [NBUF]      used on the leader CTA (2 x 256 epilogue threads)
+  uint64_t* t_empty = t_full + NBUF;          // [NBUF]      used on the leader CTA (2 x 8 epilogue warps)
   uint64_t* w_full = t_empty + NBUF;          // leader: weights of both CTAs landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);
@@ -75,9 +75,11 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     ptx::prefetch_tmap(&tmap_wgt);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 2); ptx::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NBUF; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 2 * 32 * kEpiWarps); }
-    ptx::mbar_init(w_full, 2);
+    // a_full / w_full live on the leader: ONE arrival (its own arrive.expect_tx for the bytes of BOTH CTAs); the peer's
+    // TMA only contributes complete_tx bytes (a transiently negative tx-count is legal), so no remote arrive is needed
+    for (int i = 0; i < A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 2 * kEpiWarps); }
+    ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
@@ -99,7 +101,6 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     if (lane == 0) {
       // resident weights of this cluster's class, N-half of this rank
       if (rank == 0) ptx::mbar_expect_tx(w_full, 2 * W_BYTES);
-      else ptx::mbar_arrive_cluster(w_full, 0);
       const int wrow0 = (q * 2 + (int)rank) * (W_BYTES / 128);
 #pragma unroll
       for (int j = 0; j < W_BYTES / 32768; ++j)
@@ -116,7 +117,6 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
               const int as = a_it % A_STAGES;
               ptx::mbar_wait(&a_empty[as], ((a_it / A_STAGES) & 1) ^ 1);
               if (rank == 0) ptx::mbar_expect_tx(&a_full[as], 2 * A_BYTES);
-              else ptx::mbar_arrive_cluster(&a_full[as], 0);
               ptx::tma_load_5d_2sm(smem_a + as * A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, r, id);
             }
           }
@@ -255,8 +255,11 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
         }
         ptx::tc_fence_before();
-        if (rank == 0) ptx::mbar_arrive(&t_empty[buf]);
-        else ptx::mbar_arrive_cluster(&t_empty[buf], 0);
+        __syncwarp();                      // every lane's tcgen05.ld has completed: one arrive per warp
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(&t_empty[buf]);
+          else ptx::mbar_arrive_cluster(&t_empty[buf], 0);
+        }
       }
     }
   }

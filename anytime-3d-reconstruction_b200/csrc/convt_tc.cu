@@ -14,7 +14,7 @@
 // delta_w via the start address of the UMMA shared-memory descriptor.  The out-of-bounds fill of TMA is the
 // 'same' padding.  delta_w = 0 feeds both pw parities in a single MMA of N = 2*COUT.
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = epilogue
+// Roles (384 threads): warps 0..7 = epilogue, warp 8 = TMEM allocator, warp 10 = TMA producer, warp 11 = MMA issuer
 // (tcgen05.ld -> scale/shift -> activation -> 16-bit -> global; warps e and e+4 split the columns).  Accumulators are double-buffered in TMEM so the
 // epilogue of unit i overlaps the main loop of unit i + 1.  Persistent CTAs, static round-robin unit schedule.
 #include <cstdlib>
@@ -35,7 +35,8 @@ struct Cfg {
   static constexpr bool PWB = (COUT <= 128);              // both pw parities in one unit
   static constexpr int NPAR = PWB ? 4 : 8;                // parity classes per position
   static constexpr int NACC = PWB ? 2 * COUT : COUT;      // fp32 accumulator columns per unit
-  static constexpr int TMEM_COLS = (2 * NACC <= 256) ? 256 : 512;
+  static constexpr int NBUF = 512 / NACC;                 // accumulator buffers in TMEM (4 for Cout = 64, else 2)
+  static constexpr int TMEM_COLS = 512;
   static constexpr int CHUNKS = CIN / 64;                 // 64-channel K chunks
   static constexpr int A_BYTES = (WIN + 2) * NT * 128;    // one input row incl. halo, one chunk
   static constexpr int BROWS = PWB ? 4 * COUT : 2 * COUT; // weight rows per (sd, sh, chunk)
@@ -46,15 +47,18 @@ struct Cfg {
   static constexpr int A_STAGES = (TUNE == 0) ? 3 : (COUT == 64 ? 5 : (COUT == 128 ? 4 : 3));
   static constexpr int B_STAGES = (TUNE == 0) ? ((COUT == 256) ? 3 : 4) : 4;
   static constexpr int OUT_STAGE_BYTES = STAGED_STORES ? 8 * 4096 : 0;   // 32 rows x 128 B per epilogue warp
-  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 2 * NBUF;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + OUT_STAGE_BYTES +
                                     NUM_BARS * 8 + 16 + 2 * NACC * 4;
   static_assert(BROWS % BSLOT_ROWS == 0, "weight rows per input row must fill whole slots");
   static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
 };
 
-constexpr int kEpiWarps = 8;                 // 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
+constexpr int kEpiWarps = 8;                 // warps 0..7, 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
 constexpr int kThreads = 128 + 32 * kEpiWarps;
+// The warp arbiter favours higher warp ids: the latency-critical single-thread roles get the top ids so the epilogue
+// warps sharing their schedulers cannot starve them.
+constexpr int kWarpAlloc = 8, kWarpTma = 10, kWarpMma = 11;
 
 template <class C, int FMT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -76,8 +80,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint64_t* b_full = a_empty + C::A_STAGES;
   uint64_t* b_empty = b_full + C::B_STAGES;
   uint64_t* t_full = b_empty + C::B_STAGES;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_empty = t_full + C::NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + C::NBUF);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned: bars are 8 B, +16 B slot
   float* s_shift = s_scale + NACC;
 
@@ -85,17 +89,17 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   const int lane = threadIdx.x & 31;
   const int total_units = n_blocks * WIN * WIN * C::NPAR;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     ptx::prefetch_tmap(&tmap_act);
     ptx::prefetch_tmap(&tmap_wgt);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < C::A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::B_STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 32 * kEpiWarps); }
+    for (int i = 0; i < C::NBUF; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 32 * kEpiWarps); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     ptx::tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
     ptx::tmem_relinquish<1>();
   }
@@ -108,7 +112,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     // ===================================================== TMA producer
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
@@ -144,7 +148,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===================================================== MMA issuer: the whole warp stays converged (so descriptors and
     // addresses live in uniform registers); only tcgen05.mma / commit are predicated on one elected lane
     {
@@ -160,8 +164,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
         const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
         const int pw = par & 1;  // only meaningful when !PWB
-        const int buf = unit_it & 1;
-        ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
+        const int buf = unit_it % C::NBUF;
+        ptx::mbar_wait(&t_empty[buf], ((unit_it / C::NBUF) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * NACC;
         uint32_t accum = 0;
@@ -226,9 +230,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < kEpiWarps) {
     // ===================================================== epilogue: TMEM -> BN/act -> 16-bit -> global
-    const int e = warp - 4;
+    const int e = warp;
     const int quarter = e & 3;                         // TMEM lane quarter this warp may read (== warp % 4)
     const int chalf = e >> 2;                          // which half of the accumulator columns
     const int row = quarter * 32 + lane;               // TMEM lane == GEMM row
@@ -243,8 +247,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       const int h = pos % WIN, d = (pos / WIN) % WIN, nb = pos / (WIN * WIN);
       const int pd = C::PWB ? (par >> 1) : (par >> 2);
       const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
-      const int buf = unit_it & 1;
-      ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
+      const int buf = unit_it % C::NBUF;
+      ptx::mbar_wait(&t_full[buf], (unit_it / C::NBUF) & 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * NACC + chalf * NCOLS;
       uint8_t* stage = smem_o + e * 4096;               // this warp's 32 rows x 128 B staging tile
@@ -324,7 +328,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+  if (warp == kWarpAlloc) ptx::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
 }
 
 template <class C>
