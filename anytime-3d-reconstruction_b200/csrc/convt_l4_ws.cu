@@ -24,7 +24,8 @@ namespace {
 
 constexpr int COUT = 64, WIN = 16, NT = 8, NACC = 128, CHUNKS = 2;
 constexpr int A_BYTES = (WIN + 2) * NT * 128;   // 18432
-constexpr int A_STAGES = 5;
+constexpr int A_STAGES = 4;
+constexpr int OUT_STAGE_BYTES = 8 * 2048;        // per epilogue warp: 32 rows x 64 B (32 channels), XOR-swizzled
 constexpr int SLICE_BYTES = 128 * 128;          // one (sd, sh, chunk) slice of one rank
 constexpr int W_BYTES = 8 * SLICE_BYTES;        // 131072
 constexpr int NBUF = 4;                         // two units accumulate while older ones drain
@@ -32,7 +33,7 @@ constexpr int TMEM_COLS = NBUF * NACC;          // 512
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int NUM_BARS = 2 * A_STAGES + 2 * NBUF + 1;
-constexpr int SMEM_BYTES = 1024 + W_BYTES + A_STAGES * A_BYTES + NUM_BARS * 8 + 16 + 2 * NACC * 4;
+constexpr int SMEM_BYTES = 1024 + W_BYTES + A_STAGES * A_BYTES + OUT_STAGE_BYTES + NUM_BARS * 8 + 16 + 2 * NACC * 4;
 
 // Schedule.  Cluster c owns parity class q = c % 4 for the whole launch (weights loaded once) and, together with the
 // other clusters of its class, walks the items t = (decode-block pair, d).  An item is a sweep over h = 0..15: the
@@ -50,7 +51,8 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + A_STAGES * A_BYTES);
+  uint8_t* smem_o = smem_a + A_STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + OUT_STAGE_BYTES);
   uint64_t* a_full = bars;                    // [A_STAGES]  used on the leader CTA (1 arrival + both CTAs' bytes)
   uint64_t* a_empty = a_full + A_STAGES;      // [A_STAGES]  per CTA, multicast commit
   uint64_t* t_full = a_empty + A_STAGES;      // [NBUF]      per CTA, multicast commit
@@ -210,16 +212,15 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     const int chalf = e >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int w = row / NT;
-    const int nloc = row % NT;
     constexpr int OD = 2 * WIN;
     constexpr int NCOLS = NACC / 2;   // 64 columns = one pw parity per warp
     const int pw = chalf;
+    uint8_t* stage = smem_o + e * 2048;
+    (void)row;
     uint32_t u = 0;
     for (int t = cj; t < n_items; t += n_per_class) {
       const int d = t % WIN;
       const int nb = 2 * (t / WIN) + (int)rank;
-      const int n = nb * NT + nloc;
       for (int h = 0; h < WIN; ++h, ++u) {
         const int buf = u % NBUF;
         ptx::mbar_wait(&t_full[buf], (u / NBUF) & 1);
@@ -245,14 +246,26 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             o[2 * k] = pack2<FMT>(x0, x1);
             o[2 * k + 1] = pack2<FMT>(x2, x3);
           }
-          if (n < n_alloc) {
-            const size_t vox = (((size_t)n * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * w + pw);
-            uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + co);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-            dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+          // lane = row: 4 x 16 B into a 64-byte staging row (chunks swizzled by row pairs, conflict-free) ...
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            *reinterpret_cast<uint4*>(stage + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) * 16)) =
+                make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          __syncwarp();
+          // ... then 4 lanes per row: every warp-level store writes 8 contiguous 64-byte half-lines
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int c16 = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c16 ^ ((r >> 1) & 3)) * 16));
+            const int grow = quarter * 32 + r;
+            const int wr = grow / NT, nr = nb * NT + grow % NT;
+            if (nr < n_alloc) {
+              const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
+              *reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8) = val;
+            }
           }
+          __syncwarp();
         }
         ptx::tc_fence_before();
         __syncwarp();                      // every lane's tcgen05.ld has completed: one arrive per warp

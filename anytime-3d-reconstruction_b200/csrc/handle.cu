@@ -99,8 +99,8 @@ struct a3d_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
   int sticky = 0;
-  bool l4_generic = true;    // A3D_L4_IMPL=ws selects the 2-CTA weight-stationary kernel for the 128->64 layer
-                             // (parity-identical; currently ~8 % slower than the generic 1-CTA kernel)
+  bool l4_generic = false;   // A3D_L4_IMPL=generic: run the 128->64 layer on the generic 1-CTA kernel instead of the
+                             // 2-CTA weight-stationary one (parity-identical, ~15 % slower: shared-memory-bandwidth bound)
 };
 
 namespace {
@@ -471,7 +471,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   h->dense_units = h->grid0 * h->grid0 * h->grid0 * h->ch0;  // :120
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
-  { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = !(e && std::string(e) == "ws"); }
+  { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = e && std::string(e) == "generic"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
   h->act_elems[0] = 512; h->act_elems[1] = 64 * 512; h->act_elems[2] = 512 * 256; h->act_elems[3] = 4096 * 128;
