@@ -1,6 +1,6 @@
 // Stride-2 transposed 3-D convolution (k = 4, padding 'same') + folded BatchNorm + activation as a tcgen05
 // implicit GEMM for sm_100a.  Replaces conv3DDec(), /root/reference/src/net_core/autoencoder3D.py:41-54, for the
-// three stride-2 hidden layers (512->256, 256->128, 128->64).
+// stride-2 hidden layers (512->256, 256->128; the 128->64 layer normally runs in convt_l4_ws.cu).
 //
 // Formulation.  Output voxel o = 2j + p (p = parity per axis) receives input voxels j + delta with tap
 // t = p + 1 - 2*delta:   p = 0: delta in {-1, 0} (taps 3, 1);   p = 1: delta in {0, +1} (taps 2, 0).
@@ -14,9 +14,18 @@
 // delta_w via the start address of the UMMA shared-memory descriptor.  The out-of-bounds fill of TMA is the
 // 'same' padding.  delta_w = 0 feeds both pw parities in a single MMA of N = 2*COUT.
 //
+// PAIR = 2 (default for 512->256 and 256->128): two CTAs of a cluster run the same (d, h, parity class) on two adjacent
+// decode blocks as ONE tcgen05 cta_group::2 MMA of M = 256.  They share every weight tile: each CTA loads and holds
+// only its N-half (contiguous row ranges of the repacked weights), which halves the TMA weight writes and the
+// B-operand reads -- these layers are bound by shared-memory bandwidth (MMA operand reads + TMA writes), not by the
+// tensor pipe.  PAIR = 1 keeps the single-CTA path (A3D_CONV_PAIR=1, and the 128->64 layer with A3D_L4_IMPL=generic).
+//
 // Roles (384 threads): warps 0..7 = epilogue, warp 8 = TMEM allocator, warp 10 = TMA producer, warp 11 = MMA issuer
-// (tcgen05.ld -> scale/shift -> activation -> 16-bit -> global; warps e and e+4 split the columns).  Accumulators are double-buffered in TMEM so the
-// epilogue of unit i overlaps the main loop of unit i + 1.  Persistent CTAs, static round-robin unit schedule.
+// (converged warp; only tcgen05.mma / commit are predicated on an elected lane, so descriptors stay in uniform
+// registers).  fp32 accumulators are multi-buffered in TMEM (512 columns) so the epilogue of unit i overlaps the main
+// loop of unit i + 1.  Epilogue: tcgen05.ld -> scale/shift -> activation -> 16-bit -> XOR-swizzled 128-byte staging
+// rows in shared memory -> every warp-level store writes four complete 128-byte lines.  Persistent CTAs, static
+// round-robin unit schedule with the parity class of a CTA (pair) fixed.
 #include <cstdlib>
 
 #include "epilogue.cuh"
@@ -27,10 +36,9 @@ namespace a3d {
 
 namespace {
 
-template <int CIN_, int COUT_, int WIN_, int TUNE_ = 0>
+template <int CIN_, int COUT_, int WIN_, int PAIR_>
 struct Cfg {
-  static constexpr int TUNE = TUNE_;
-  static constexpr int CIN = CIN_, COUT = COUT_, WIN = WIN_;
+  static constexpr int CIN = CIN_, COUT = COUT_, WIN = WIN_, PAIR = PAIR_;
   static constexpr int NT = 128 / WIN;                    // decodes per unit
   static constexpr bool PWB = (COUT <= 128);              // both pw parities in one unit
   static constexpr int NPAR = PWB ? 4 : 8;                // parity classes per position
@@ -40,33 +48,31 @@ struct Cfg {
   static constexpr int CHUNKS = CIN / 64;                 // 64-channel K chunks
   static constexpr int A_BYTES = (WIN + 2) * NT * 128;    // one input row incl. halo, one chunk
   static constexpr int BROWS = PWB ? 4 * COUT : 2 * COUT; // weight rows per (sd, sh, chunk)
-  static constexpr int BSLOT_ROWS = 256;
+  static constexpr int BSLOT_ROWS = 256;                  // weight rows per slot (whole MMA groups)
   static constexpr int BSLOTS = BROWS / BSLOT_ROWS;       // weight slots per input row
-  static constexpr int B_BYTES = BSLOT_ROWS * 128;
-  static constexpr bool STAGED_STORES = (TUNE == 0);
-  static constexpr int A_STAGES = (TUNE == 0) ? 3 : (COUT == 64 ? 5 : (COUT == 128 ? 4 : 3));
-  static constexpr int B_STAGES = (TUNE == 0) ? ((COUT == 256) ? 3 : 4) : 4;
-  static constexpr int OUT_STAGE_BYTES = STAGED_STORES ? 8 * 4096 : 0;   // 32 rows x 128 B per epilogue warp
+  static constexpr int B_BYTES = BSLOT_ROWS * 128 / PAIR; // bytes of a slot held by ONE CTA
+  static constexpr int A_STAGES = (PAIR == 2) ? 4 : 3;
+  static constexpr int B_STAGES = (PAIR == 2) ? 5 : ((COUT == 256) ? 3 : 4);
+  static constexpr int OUT_STAGE_BYTES = 8 * 4096;        // 32 rows x 128 B per epilogue warp
   static constexpr int NUM_BARS = 2 * A_STAGES + 2 * B_STAGES + 2 * NBUF;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_STAGES * A_BYTES + B_STAGES * B_BYTES + OUT_STAGE_BYTES +
                                     NUM_BARS * 8 + 16 + 2 * NACC * 4;
   static_assert(BROWS % BSLOT_ROWS == 0, "weight rows per input row must fill whole slots");
   static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
+  static_assert(!(PAIR == 2 && COUT == 64), "the 128->64 layer has its own 2-CTA kernel (convt_l4_ws.cu)");
 };
 
 constexpr int kEpiWarps = 8;                 // warps 0..7, 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
 constexpr int kThreads = 128 + 32 * kEpiWarps;
-// The warp arbiter favours higher warp ids: the latency-critical single-thread roles get the top ids so the epilogue
-// warps sharing their schedulers cannot starve them.
 constexpr int kWarpAlloc = 8, kWarpTma = 10, kWarpMma = 11;
 
 template <class C, int FMT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
                    uint16_t* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int n_blocks, int n_alloc, int dbg) {
-  constexpr int CIN = C::CIN, COUT = C::COUT, WIN = C::WIN, NT = C::NT, NACC = C::NACC;
-  (void)CIN;
+                   int n_blocks, int n_alloc) {
+  constexpr int COUT = C::COUT, WIN = C::WIN, NT = C::NT, NACC = C::NACC, PAIR = C::PAIR;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle, computed on the shared-window address so the pointer keeps its
   // __shared__ provenance (LDS/STS instead of generic LD/ST)
@@ -75,51 +81,58 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint8_t* smem_b = smem + C::A_STAGES * C::A_BYTES;
   uint8_t* smem_o = smem_b + C::B_STAGES * C::B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + C::OUT_STAGE_BYTES);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + C::A_STAGES;
+  uint64_t* a_full = bars;                       // PAIR = 2: used on the leader CTA (bytes of both CTAs)
+  uint64_t* a_empty = a_full + C::A_STAGES;      // per CTA (multicast commit)
   uint64_t* b_full = a_empty + C::A_STAGES;
   uint64_t* b_empty = b_full + C::B_STAGES;
-  uint64_t* t_full = b_empty + C::B_STAGES;
-  uint64_t* t_empty = t_full + C::NBUF;
+  uint64_t* t_full = b_empty + C::B_STAGES;      // per CTA (multicast commit)
+  uint64_t* t_empty = t_full + C::NBUF;          // PAIR = 2: used on the leader CTA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + C::NBUF);
-  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned: bars are 8 B, +16 B slot
+  float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_shift = s_scale + NACC;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_units = n_blocks * WIN * WIN * C::NPAR;
+  const int rank = (PAIR == 2) ? (int)ptx::cluster_ctarank() : 0;
+  const int cl_id = blockIdx.x / PAIR;           // cluster (or CTA) index
+  const int n_cl = gridDim.x / PAIR;
+  const int nb_groups = (n_blocks + PAIR - 1) / PAIR;
+  const int total_units = nb_groups * WIN * WIN * C::NPAR;
 
   if (warp == kWarpTma && lane == 0) {
     ptx::prefetch_tmap(&tmap_act);
     ptx::prefetch_tmap(&tmap_wgt);
   }
   if (warp == kWarpMma && lane == 0) {
+    // full barriers take ONE arrival: the (leader's) arrive.expect_tx for the bytes of all CTAs of the pair; the
+    // peer's TMA only contributes complete_tx bytes (a transiently negative tx-count is legal)
     for (int i = 0; i < C::A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::B_STAGES; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < C::NBUF; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 32 * kEpiWarps); }
+    for (int i = 0; i < C::NBUF; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], PAIR * kEpiWarps); }
     ptx::fence_barrier_init();
-  }
-  if (warp == kWarpAlloc) {
-    ptx::tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
-    ptx::tmem_relinquish<1>();
   }
   for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
     s_scale[i] = scale[i % COUT];
     s_shift[i] = shift[i % COUT];
   }
+  if constexpr (PAIR == 2) ptx::cluster_sync_all();   // barrier inits visible before any remote arrive / multicast
+  if (warp == kWarpAlloc) {
+    ptx::tmem_alloc<PAIR>(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish<PAIR>();
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kWarpTma) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = cl_id; u < total_units; u += n_cl) {
         const int par = u % C::NPAR;
         const int pos = u / C::NPAR;
-        const int h = pos % WIN, d = (pos / WIN) % WIN, nb = pos / (WIN * WIN);
+        const int h = pos % WIN, d = (pos / WIN) % WIN, nb = (pos / (WIN * WIN)) * PAIR + rank;
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
         const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
         for (int sd = 0; sd < 2; ++sd) {
@@ -131,16 +144,31 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             for (int c = 0; c < C::CHUNKS; ++c) {
               const int as = a_it % C::A_STAGES;
               ptx::mbar_wait(&a_empty[as], ((a_it / C::A_STAGES) & 1) ^ 1);
-              ptx::mbar_expect_tx(&a_full[as], C::A_BYTES);
-              ptx::tma_load_5d(smem_a + as * C::A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, ih, id);
+              if (rank == 0) ptx::mbar_expect_tx(&a_full[as], PAIR * C::A_BYTES);
+              if constexpr (PAIR == 2)
+                ptx::tma_load_5d_2sm(smem_a + as * C::A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, ih, id);
+              else
+                ptx::tma_load_5d(smem_a + as * C::A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, ih, id);
               ++a_it;
               const int row0 = ((((par * 2 + sd) * 2 + sh) * C::CHUNKS) + c) * C::BROWS;
 #pragma unroll
               for (int j = 0; j < C::BSLOTS; ++j) {
                 const int bs = b_it % C::B_STAGES;
+                uint8_t* dst = smem_b + bs * C::B_BYTES;
                 ptx::mbar_wait(&b_empty[bs], ((b_it / C::B_STAGES) & 1) ^ 1);
-                ptx::mbar_expect_tx(&b_full[bs], C::B_BYTES);
-                ptx::tma_load_2d(smem_b + bs * C::B_BYTES, &tmap_wgt, &b_full[bs], 0, row0 + j * C::BSLOT_ROWS);
+                if (rank == 0) ptx::mbar_expect_tx(&b_full[bs], PAIR * C::B_BYTES);
+                const int r0 = row0 + j * C::BSLOT_ROWS;
+                if constexpr (PAIR == 1) {
+                  ptx::tma_load_2d(dst, &tmap_wgt, &b_full[bs], 0, r0);
+                } else if (C::PWB && j == 1) {
+                  // COUT = 128, slot 1: dw=-1 tile rows [0,128), dw=+1 tile rows [128,256): this CTA's 64-row N-halves
+                  ptx::tma_load_2d_2sm(dst, &tmap_wgt, &b_full[bs], 0, r0 + rank * 64);
+                  ptx::tma_load_2d_2sm(dst + 64 * 128, &tmap_wgt, &b_full[bs], 0, r0 + 128 + rank * 64);
+                } else {
+                  // one N = 256 MMA: this CTA's N-half = 128 contiguous rows (two 64-row boxes)
+                  ptx::tma_load_2d_2sm(dst, &tmap_wgt, &b_full[bs], 0, r0 + rank * 128);
+                  ptx::tma_load_2d_2sm(dst + 64 * 128, &tmap_wgt, &b_full[bs], 0, r0 + rank * 128 + 64);
+                }
                 ++b_it;
               }
             }
@@ -149,15 +177,15 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       }
     }
   } else if (warp == kWarpMma) {
-    // ===================================================== MMA issuer: the whole warp stays converged (so descriptors and
-    // addresses live in uniform registers); only tcgen05.mma / commit are predicated on one elected lane
-    {
+    // ===================================================== MMA issuer (leader CTA only when PAIR = 2)
+    if (rank == 0) {
       uint32_t a_it = 0, b_it = 0, unit_it = 0;
-      constexpr uint32_t idesc_full = ptx::make_idesc_f16(128, NACC > 256 ? 256 : NACC, FMT);
-      constexpr uint32_t idesc_half = ptx::make_idesc_f16(128, COUT, FMT);
+      constexpr int MM = 128 * PAIR;
+      constexpr uint32_t idesc_full = ptx::make_idesc_f16(MM, NACC > 256 ? 256 : NACC, FMT);
+      constexpr uint32_t idesc_half = ptx::make_idesc_f16(MM, COUT, FMT);
       const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
       const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+      for (int u = cl_id; u < total_units; u += n_cl, ++unit_it) {
         const int par = u % C::NPAR;
         const int pos = u / C::NPAR;
         const int h = pos % WIN, d = (pos / WIN) % WIN;
@@ -186,37 +214,40 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                 ptx::tc_fence_after();
                 const uint32_t b_lo = b_lo0 + bs * (C::B_BYTES >> 4);
                 constexpr uint32_t W1 = (NT * 128) >> 4;       // one position along w, in 16-byte units
+                // offsets (>> 4) of the B tiles inside this CTA's part of the slot
+                constexpr uint32_t BB = ((2 * COUT / PAIR) * 128) >> 4;   // COUT = 64: start of the dw = -1 tile
+                constexpr uint32_t BC = ((3 * COUT / PAIR) * 128) >> 4;   // COUT = 64: start of the dw = +1 tile
+                constexpr uint32_t BH = ((COUT / PAIR) * 128) >> 4;       // COUT = 128, slot 1: start of the dw = +1 tile
                 if (ptx::elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint32_t ko = kk * 2;  // 16 elements * 2 bytes inside the 128-byte swizzled row, >> 4
-                  if constexpr (C::PWB && C::BSLOTS == 1) {
-                    // COUT = 64: [0,128) = (pw0,tw1 | pw1,tw2) dw=0; [128,192) = pw0,tw3 dw=-1; [192,256) = pw1,tw0 dw=+1
-                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
-                                     (kk == 0) ? accum : 1u);
-                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ((2 * COUT * 128) >> 4) + ko),
-                                     idesc_half, 1);
-                    ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
-                                     ptx::sw128_desc(b_lo + ((3 * COUT * 128) >> 4) + ko), idesc_half, 1);
-                  } else if constexpr (C::PWB) {
-                    // COUT = 128: slot 0 = (pw0,tw1 | pw1,tw2) dw=0 (N = 256); slot 1 = pw0,tw3 dw=-1 | pw1,tw0 dw=+1
-                    if (j == 0) {
-                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
-                                       (kk == 0) ? accum : 1u);
+                  for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t ko = kk * 2;  // 16 elements * 2 bytes inside the 128-byte swizzled row, >> 4
+                    if constexpr (C::PWB && C::BSLOTS == 1) {
+                      // COUT = 64: (pw0,tw1 | pw1,tw2) dw=0, N = 128;  pw0,tw3 dw=-1;  pw1,tw0 dw=+1
+                      ptx::umma_f16<PAIR>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                          (kk == 0) ? accum : 1u);
+                      ptx::umma_f16<PAIR>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + BB + ko), idesc_half, 1);
+                      ptx::umma_f16<PAIR>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
+                                          ptx::sw128_desc(b_lo + BC + ko), idesc_half, 1);
+                    } else if constexpr (C::PWB) {
+                      // COUT = 128: slot 0 = (pw0,tw1 | pw1,tw2) dw=0 (N = 256); slot 1 = pw0,tw3 dw=-1 | pw1,tw0 dw=+1
+                      if (j == 0) {
+                        ptx::umma_f16<PAIR>(tacc, ptx::sw128_desc(a_lo + W1 + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                            (kk == 0) ? accum : 1u);
+                      } else {
+                        ptx::umma_f16<PAIR>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ko), idesc_half, 1);
+                        ptx::umma_f16<PAIR>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
+                                            ptx::sw128_desc(b_lo + BH + ko), idesc_half, 1);
+                      }
                     } else {
-                      ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + ko), ptx::sw128_desc(b_lo + ko), idesc_half, 1);
-                      ptx::umma_f16<1>(tacc + COUT, ptx::sw128_desc(a_lo + 2 * W1 + ko),
-                                       ptx::sw128_desc(b_lo + ((COUT * 128) >> 4) + ko), idesc_half, 1);
+                      // COUT = 256, one pw per unit: slot 0 = dw=0 tap, slot 1 = dw=+-1 tap
+                      const uint32_t a_off = (j == 0) ? W1 : (pw ? 2 * W1 : 0);
+                      ptx::umma_f16<PAIR>(tacc, ptx::sw128_desc(a_lo + a_off + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
+                                          (kk == 0) ? accum : 1u);
                     }
-                  } else {
-                    // COUT = 256, one pw per unit: slot 0 = dw=0 tap, slot 1 = dw=+-1 tap
-                    const uint32_t a_off = (j == 0) ? W1 : (pw ? 2 * W1 : 0);
-                    ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + a_off + ko), ptx::sw128_desc(b_lo + ko), idesc_full,
-                                     (kk == 0) ? accum : 1u);
                   }
-                }
-                ptx::umma_commit<1>(&b_empty[bs]);  // slot reusable once these MMAs retire
-                if (j == C::BSLOTS - 1) ptx::umma_commit<1>(&a_empty[as]);
+                  ptx::umma_commit<PAIR>(&b_empty[bs]);  // slot reusable (in both CTAs) once these MMAs retire
+                  if (j == C::BSLOTS - 1) ptx::umma_commit<PAIR>(&a_empty[as]);
                 }
                 __syncwarp();
                 if (j == 0) accum = 1;
@@ -226,32 +257,30 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             }
           }
         }
-        if (ptx::elect_one()) ptx::umma_commit<1>(&t_full[buf]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit<PAIR>(&t_full[buf]);  // accumulators complete -> epilogue(s)
         __syncwarp();
       }
     }
   } else if (warp < kEpiWarps) {
-    // ===================================================== epilogue: TMEM -> BN/act -> 16-bit -> global
+    // ===================================================== epilogue: TMEM -> BN/act -> 16-bit -> smem staging -> global
     const int e = warp;
     const int quarter = e & 3;                         // TMEM lane quarter this warp may read (== warp % 4)
     const int chalf = e >> 2;                          // which half of the accumulator columns
-    const int row = quarter * 32 + lane;               // TMEM lane == GEMM row
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     constexpr int OD = 2 * WIN;
     constexpr int NCOLS = NACC / 2;                    // columns per warp
-    (void)row;
+    uint8_t* stage = smem_o + e * 4096;                // this warp's 32 rows x 128 B staging tile
     uint32_t unit_it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+    for (int u = cl_id; u < total_units; u += n_cl, ++unit_it) {
       const int par = u % C::NPAR;
       const int pos = u / C::NPAR;
-      const int h = pos % WIN, d = (pos / WIN) % WIN, nb = pos / (WIN * WIN);
+      const int h = pos % WIN, d = (pos / WIN) % WIN, nb = (pos / (WIN * WIN)) * PAIR + rank;
       const int pd = C::PWB ? (par >> 1) : (par >> 2);
       const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
       const int buf = unit_it % C::NBUF;
       ptx::mbar_wait(&t_full[buf], (unit_it / C::NBUF) & 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * NACC + chalf * NCOLS;
-      uint8_t* stage = smem_o + e * 4096;               // this warp's 32 rows x 128 B staging tile
 #pragma unroll 1
       for (int ch = 0; ch < NCOLS / 64; ++ch) {         // 64 output channels (128 B per row) at a time
         const int col0 = chalf * NCOLS + ch * 64;
@@ -268,28 +297,13 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 sc = sc4[i], sh = sh4[i];
-            float x0 = fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x);
-            float x1 = fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y);
-            float x2 = fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z);
-            float x3 = fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w);
-            if (!(dbg & 2)) { x0 = activate<ACT>(x0); x1 = activate<ACT>(x1); x2 = activate<ACT>(x2); x3 = activate<ACT>(x3); }
+            const float x0 = activate<ACT>(fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x));
+            const float x1 = activate<ACT>(fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y));
+            const float x2 = activate<ACT>(fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z));
+            const float x3 = activate<ACT>(fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w));
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
           }
-          if constexpr (!C::STAGED_STORES) {
-            // direct: this lane's row, 64 contiguous bytes
-            const int grow = quarter * 32 + lane;
-            const int wr = grow / NT, nr = nb * NT + grow % NT;
-            const int pw_ = C::PWB ? (col / COUT) : (par & 1);
-            if (nr < n_alloc && !(dbg & 1)) {
-              const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw_);
-              uint4* dst = reinterpret_cast<uint4*>(out + vox * COUT + (col % COUT));
-              dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-              dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-              dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
-            }
-          } else {
           // lane = row: 4 x 16 B into the row's 128-byte line, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
@@ -297,54 +311,70 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) =
                 make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
           }
+        }
+        if (ch == NCOLS / 64 - 1) {
+          // all TMEM reads of this warp for the unit are done: release the accumulator buffer (one arrive per warp)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) ptx::mbar_arrive(&t_empty[buf]);
+            else ptx::mbar_arrive_cluster(&t_empty[buf], 0);
           }
         }
-        if constexpr (C::STAGED_STORES) {
         __syncwarp();
         // 8 lanes per row: every warp-level store writes four complete 128-byte lines
         const int pw = C::PWB ? (col0 / COUT) : (par & 1);
         const int co = col0 % COUT;
-        if (!(dbg & 1)) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + (lane >> 3);
-            const int c16 = lane & 7;
-            const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c16 ^ (r & 7)) * 16));
-            const int grow = quarter * 32 + r;
-            const int wr = grow / NT, nr = nb * NT + grow % NT;
-            if (nr < n_alloc) {
-              const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
-              *reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8) = val;
-            }
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int c16 = lane & 7;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c16 ^ (r & 7)) * 16));
+          const int grow = quarter * 32 + r;
+          const int wr = grow / NT, nr = nb * NT + grow % NT;
+          if (nr < n_alloc) {
+            const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
+            *reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8) = val;
           }
         }
         __syncwarp();
-        }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&t_empty[buf]);
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == kWarpAlloc) ptx::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+  if constexpr (PAIR == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == kWarpAlloc) ptx::tmem_dealloc<PAIR>(tmem_base, C::TMEM_COLS);
 }
 
 template <class C>
 int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                cudaStream_t st) {
+  constexpr int PAIR = C::PAIR;
   const int n_blocks = (int)((n + C::NT - 1) / C::NT);
-  const int total_units = n_blocks * C::WIN * C::WIN * C::NPAR;
-  int grid = num_sms < total_units ? num_sms : total_units;
-  // keep the parity class of a CTA fixed across its units (weights of one class stay hot in L2 / same rows)
-  if (grid > C::NPAR) grid -= grid % C::NPAR;
-  static const int dbg = getenv("A3D_DEBUG_FLAGS") ? atoi(getenv("A3D_DEBUG_FLAGS")) : 0;
+  const int total_units = ((n_blocks + PAIR - 1) / PAIR) * C::WIN * C::WIN * C::NPAR;
+  int n_cl = num_sms / PAIR;
+  if (n_cl > total_units) n_cl = total_units;
+  // keep the parity class of a CTA (pair) fixed across its units (weights of one class stay hot in L2)
+  if (n_cl > C::NPAR) n_cl -= n_cl % C::NPAR;
+  if (n_cl < 1) n_cl = 1;
+  const CUtensorMap& tw = (PAIR == 2) ? L.tmap_wgt64 : L.tmap_wgt;
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    kern<<<grid, kThreads, C::SMEM_BYTES, st>>>(L.tmap_act, L.tmap_wgt, reinterpret_cast<uint16_t*>(out), L.scale,
-                                                L.shift, n_blocks, (int)n_alloc, dbg);
-    A3D_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_cl * PAIR);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    A3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, L.tmap_act, tw, reinterpret_cast<uint16_t*>(out),
+                                   (const float*)L.scale, (const float*)L.shift, n_blocks, (int)n_alloc));
     return A3D_OK;
   };
   if (fmt == A3D_DTYPE_F16) {
@@ -366,25 +396,24 @@ int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fm
 }  // namespace
 
 size_t convt_tc_smem_bytes(int cin, int cout, int win) {
-  if (cin == 512 && cout == 256 && win == 4) return Cfg<512, 256, 4>::SMEM_BYTES;
-  if (cin == 256 && cout == 128 && win == 8) return Cfg<256, 128, 8>::SMEM_BYTES;
-  if (cin == 128 && cout == 64 && win == 16) return Cfg<128, 64, 16>::SMEM_BYTES;
+  if (cin == 512 && cout == 256 && win == 4) return Cfg<512, 256, 4, 2>::SMEM_BYTES;
+  if (cin == 256 && cout == 128 && win == 8) return Cfg<256, 128, 8, 2>::SMEM_BYTES;
+  if (cin == 128 && cout == 64 && win == 16) return Cfg<128, 64, 16, 1>::SMEM_BYTES;
   return 0;
 }
 
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches) {
+  static const int pair = (getenv("A3D_CONV_PAIR") && atoi(getenv("A3D_CONV_PAIR")) == 1) ? 1 : 2;
   int rc;
-  static const int tune = getenv("A3D_CONV_TUNE") ? atoi(getenv("A3D_CONV_TUNE")) : 0;
   if (L.cin == 512 && L.cout == 256 && L.win == 4)
-    rc = tune ? launch_cfg<Cfg<512, 256, 4, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
-              : launch_cfg<Cfg<512, 256, 4, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = pair == 2 ? launch_cfg<Cfg<512, 256, 4, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+                   : launch_cfg<Cfg<512, 256, 4, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else if (L.cin == 256 && L.cout == 128 && L.win == 8)
-    rc = tune ? launch_cfg<Cfg<256, 128, 8, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
-              : launch_cfg<Cfg<256, 128, 8, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = pair == 2 ? launch_cfg<Cfg<256, 128, 8, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+                   : launch_cfg<Cfg<256, 128, 8, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else if (L.cin == 128 && L.cout == 64 && L.win == 16)
-    rc = tune ? launch_cfg<Cfg<128, 64, 16, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
-              : launch_cfg<Cfg<128, 64, 16, 0>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    rc = launch_cfg<Cfg<128, 64, 16, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else {
     set_error("tcgen05 ConvT path supports (512->256,W4), (256->128,W8), (128->64,W16); got %d->%d W%d", L.cin,
               L.cout, L.win);

@@ -247,6 +247,10 @@ int make_tmaps(a3d_handle* h, int li) {
     CUresult r = enc(&L.tmap_wgt, dt, 2, L.wgt_packed, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", li, (int)r); return A3D_ERR_CUDA; }
+    cuuint32_t box64[2] = {64, 64};
+    r = enc(&L.tmap_wgt64, dt, 2, L.wgt_packed, dims, strides, box64, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights64, layer %d) failed: %d", li, (int)r); return A3D_ERR_CUDA; }
   }
   return A3D_OK;
 }

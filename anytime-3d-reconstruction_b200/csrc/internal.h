@@ -28,6 +28,7 @@ struct ConvLayer {
   // tcgen05 path
   CUtensorMap tmap_act;   // 5-D view (c, n, w, h, d) of the input activations, box (64, 128/W, W+2, 1, 1), SW128
   CUtensorMap tmap_wgt;   // 2-D view (64 ci, rows) of the per-(parity,tap,chunk) repacked weights, box (64, 256), SW128
+  CUtensorMap tmap_wgt64; // same tensor, box (64, 64): N-half loads of the 2-CTA path
   void* wgt_packed = nullptr;   // device, 16-bit
   CUtensorMap tmap_wgt_ws;      // weight-stationary 2-CTA layout (128->64 layer only)
   void* wgt_ws = nullptr;

@@ -18,7 +18,7 @@ z = dr.round_bf16(rng.standard_normal((n, 64)).astype(np.float32))
 t0 = time.time()
 ref, layers = dr.decoder_forward(st, ws, z, return_layers=True)
 print(f'oracle {time.time()-t0:.2f}s', flush=True)
-dec = a3d.decoder3D(st, max_chunk=32, operand_dtype=dt, impl=impl)
+dec = a3d.decoder3D(st, max_chunk=max(32, (n + 31) // 32 * 32), operand_dtype=dt, impl=impl)
 dec.set_weights(ws)
 t0 = time.time()
 out = dec(z)
