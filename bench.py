@@ -279,7 +279,7 @@ def main():
     decodes_per_launch = B_PER_RATE * K
     tpeak, hpeak, src = peaks()
     l4_tflops = 2.0 * L4_MACS * decodes_per_launch / (stage['l4'] * 1e-3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'convt_s2_tc_kernel<128->64, W16>', 'achieved': l4_tflops, 'peak': tpeak,
+    roofline = {'bound': 'tensor', 'kernel': 'convt_l4_ws_kernel (128->64 ConvT, 2-CTA weight-stationary)', 'achieved': l4_tflops, 'peak': tpeak,
                 'unit': 'TFLOP/s', 'frac': l4_tflops / tpeak, 'traffic': None, 'peak_source': f'{src} sustained bf16',
                 'stage_ms': stage,
                 'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12}
