@@ -27,8 +27,9 @@ import numpy as np
 from . import _capi, presets
 from ._capi import FILL, VOXELS
 
-__all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'anytime_eval', 'impute', 'getEval',
-           'pack_targets', 'iou_from_counts', 'shard_range', 'allreduce_counts']
+__all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'voxelPrecisionRecallSweep', 'binary_loss',
+           'anytime_eval', 'anytime_eval_host', 'impute', 'getEval', 'pack_targets', 'iou_from_counts', 'shard_range',
+           'allreduce_counts']
 
 
 def _torch():
@@ -301,11 +302,7 @@ def voxelPrecisionRecall(xTarget, xPred, prob: float = 0.5, decoder: Decoder3D |
     """function.py:100-115.  Returns (TP, FP, FN), each [B] float32 like the reference's float sums."""
     torch = _require_cuda()
     is_np = not isinstance(xPred, torch.Tensor)
-    if decoder is None:
-        if not _vpr_decoder:
-            from .presets import MODELNET_DECODER
-            _vpr_decoder.append(Decoder3D(MODELNET_DECODER, max_chunk=32))
-        decoder = _vpr_decoder[0]
+    decoder = decoder or _default_decoder()
     dev = decoder.device
     t = _as_dev_f32(xTarget, torch, dev)
     p = _as_dev_f32(xPred, torch, dev)
@@ -324,6 +321,54 @@ def voxelPrecisionRecall(xTarget, xPred, prob: float = 0.5, decoder: Decoder3D |
     return tp, fp, fn
 
 
+def _default_decoder():
+    if not _vpr_decoder:
+        _vpr_decoder.append(Decoder3D(presets.MODELNET_DECODER, max_chunk=32))
+    return _vpr_decoder[0]
+
+
+def voxelPrecisionRecallSweep(xTarget, xPred, thresholds, strict: bool = True, decoder: Decoder3D | None = None):
+    """Threshold sweep of the evaluation notebooks (modelnetAE3.ipynb cell 2: ``yPred > prob`` for a list of
+    thresholds).  Returns int64 counts [B, T, 3] (TP, FP, FN) as a CUDA tensor (numpy if the inputs were numpy)."""
+    torch = _require_cuda()
+    is_np = not isinstance(xPred, torch.Tensor)
+    decoder = decoder or _default_decoder()
+    dev = decoder.device
+    t = _as_dev_f32(xTarget, torch, dev)
+    p = _as_dev_f32(xPred, torch, dev)
+    B = p.shape[0]
+    V = p.numel() // max(B, 1)
+    thr = np.ascontiguousarray(thresholds, np.float32).reshape(-1)
+    cnt = torch.empty((B, len(thr), 3), dtype=torch.int64, device=dev)
+    with torch.cuda.device(decoder.device_index):
+        _capi.check(decoder._lib.a3d_counts_sweep(decoder._h, t.data_ptr(), p.data_ptr(), B, V,
+                                                  thr.ctypes.data_as(C.c_void_p), len(thr), int(strict), cnt.data_ptr(),
+                                                  _stream_ptr(torch)), 'a3d_counts_sweep')
+    return cnt.cpu().numpy() if is_np else cnt
+
+
+def binary_loss(xPred, xTarget, epsilon: float = 1e-7, gamma: float = 0.5, b_range: bool = False,
+                decoder: Decoder3D | None = None):
+    """function.py:73-82 (same argument order and defaults): weighted BCE summed over voxels, one value per object.
+    ``epsilon`` is fixed at 1e-7 and ``b_range`` at False (what every call site of the reference uses)."""
+    if b_range or abs(epsilon - 1e-7) > 1e-12:
+        raise NotImplementedError('binary_loss: only epsilon=1e-7, b_range=False (the reference call sites) are built')
+    torch = _require_cuda()
+    is_np = not isinstance(xPred, torch.Tensor)
+    decoder = decoder or _default_decoder()
+    dev = decoder.device
+    p = _as_dev_f32(xPred, torch, dev)
+    t = _as_dev_f32(xTarget, torch, dev)
+    B = p.shape[0]
+    V = p.numel() // max(B, 1)
+    loss = torch.empty((B,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(decoder.device_index):
+        _capi.check(decoder._lib.a3d_binary_loss(decoder._h, p.data_ptr(), t.data_ptr(), B, V, float(gamma),
+                                                 loss.data_ptr(), _stream_ptr(torch)), 'a3d_binary_loss')
+    out = loss.to(torch.float32)
+    return out.cpu().numpy() if is_np else out
+
+
 def iou_from_counts(counts):
     """IoU = TP / (TP + FP + FN): (mean over objects, global sum-then-ratio)."""
     c = np.asarray(counts, dtype=np.float64).reshape(-1, 3)
@@ -334,12 +379,13 @@ def iou_from_counts(counts):
 
 def anytime_eval(decoder: Decoder3D, z, mask, category_vectors, targets, K: int = 16, seed: int = 0,
                  fill: str = 'prior_sample', threshold: float = 0.5, return_grid: bool = False, obj_offset: int = 0,
-                 z_completed=None):
+                 z_completed=None, return_loss: bool = False, gamma: float = 0.6):
     """Anytime reconstruction of a batch of partially received latents, all on the GPU:
     K-sample imputation -> decoder -> mean of the K occupancy grids -> threshold -> TP/FP/FN.
 
     z, mask: [B, D]; category_vectors: [C, D]; targets: fp32 {0,1} [B,64,64,64,1] or bit-packed uint8 [B,32768].
-    Returns dict(counts [B,3] int64 CUDA tensor, z_completed [B,K,D], cstar, mean_prob (if return_grid)).
+    Returns dict(counts [B,3] int64 CUDA tensor, z_completed [B,K,D], cstar, mean_prob (if return_grid),
+    loss [B] float64 = weighted BCE of function.py:73-82 with ``gamma`` (if return_loss)).
     ``z_completed`` (already imputed [B,K,D]) skips the imputation step."""
     torch = _require_cuda()
     dev = decoder.device
@@ -358,11 +404,20 @@ def anytime_eval(decoder: Decoder3D, z, mask, category_vectors, targets, K: int 
         bits = pack_targets(decoder, targets)
     counts = torch.empty((B, 3), dtype=torch.int64, device=dev)
     grid = torch.empty((B, 64, 64, 64, 1), dtype=torch.float32, device=dev) if return_grid else None
+    loss = torch.empty((B,), dtype=torch.float64, device=dev) if return_loss else None
     with torch.cuda.device(decoder.device_index):
-        _capi.check(decoder._lib.a3d_anytime_eval(decoder._h, zc.data_ptr(), B, K, bits.data_ptr(), float(threshold),
-                                                  counts.data_ptr(), 0 if grid is None else grid.data_ptr(),
-                                                  _stream_ptr(torch)), 'a3d_anytime_eval')
+        if return_loss:
+            _capi.check(decoder._lib.a3d_anytime_eval_loss(
+                decoder._h, zc.data_ptr(), B, K, bits.data_ptr(), float(threshold), float(gamma), counts.data_ptr(),
+                loss.data_ptr(), 0 if grid is None else grid.data_ptr(), _stream_ptr(torch)), 'a3d_anytime_eval_loss')
+        else:
+            _capi.check(decoder._lib.a3d_anytime_eval(decoder._h, zc.data_ptr(), B, K, bits.data_ptr(),
+                                                      float(threshold), counts.data_ptr(),
+                                                      0 if grid is None else grid.data_ptr(), _stream_ptr(torch)),
+                        'a3d_anytime_eval')
     out = {'counts': counts, 'z_completed': zc, 'cstar': cstar}
+    if return_loss:
+        out['loss'] = loss
     if return_grid:
         out['mean_prob'] = grid
     return out
@@ -396,9 +451,9 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
 
     ``inputs = (z, output_images, category_list)`` where ``z`` are the encoder latents (the reference samples them
     from the encoder at :1463-1470; the encoder is outside this path).  Returns the reference's 10-tuple
-    ``(pred, loss_shape, pr, rc, acc_cat, pred_corr, loss_corr, pr_corr, rc_corr, acc_cat_corr)`` with
-    ``loss_shape`` = None (the weighted-BCE is not on the accelerated path) and K-sample averaging of the corrected
-    branch when K > 1."""
+    ``(pred, loss_shape, pr, rc, acc_cat, pred_corr, loss_corr, pr_corr, rc_corr, acc_cat_corr)``; ``loss_shape`` is the
+    batch mean of binary_loss(gamma=0.60) (nolbo.py:1497-1498), fused into the tail kernel; the corrected branch is
+    K-sample averaged when K > 1."""
     if training:
         raise NotImplementedError('inference only')
     torch = _require_cuda()
@@ -418,7 +473,9 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
     cat = None if category_list is None else _as_dev_f32(category_list, torch, decoder.device)
 
     def branch(fill, k):
-        r = anytime_eval(decoder, z_t, mask, mu, bits, K=k, seed=seed, fill=fill, return_grid=True)
+        r = anytime_eval(decoder, z_t, mask, mu, bits, K=k, seed=seed, fill=fill, return_grid=True, return_loss=True,
+                         gamma=0.60)
+        loss = r['loss'].mean().item()                                  # reduce_mean(axis=0) :1498
         c = r['counts'].to(torch.float64)
         pr = (c[:, 0] / (c[:, 0] + c[:, 1] + 1e-10)).mean().item()   # :1499-1501
         rc = (c[:, 0] / (c[:, 0] + c[:, 2] + 1e-10)).mean().item()
@@ -427,13 +484,13 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
             zc = r['z_completed'][:, 0, :]
             dist = ((zc[:, None, :] - mu[None]) ** 2).sum(-1)          # :1488-1494 (metric only; plumbing)
             acc = (dist.argmin(-1) == cat.argmax(-1)).float().mean().item()
-        return r['mean_prob'], pr, rc, acc
+        return r['mean_prob'], loss, pr, rc, acc
 
-    pred, pr, rc, acc = branch(fill0, 1)
+    pred, loss, pr, rc, acc = branch(fill0, 1)
     if missing_prob == 0.0:
-        return pred, None, pr, rc, acc, 0, 0, 0, 0, 0   # :1502-1503
-    pred_c, pr_c, rc_c, acc_c = branch('prior_sample', K)
-    return pred, None, pr, rc, acc, pred_c, None, pr_c, rc_c, acc_c
+        return pred, loss, pr, rc, acc, 0, 0, 0, 0, 0   # :1502-1503
+    pred_c, loss_c, pr_c, rc_c, acc_c = branch('prior_sample', K)
+    return pred, loss, pr, rc, acc, pred_c, loss_c, pr_c, rc_c, acc_c
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU plumbing

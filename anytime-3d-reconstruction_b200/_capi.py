@@ -40,6 +40,12 @@ SIGNATURES = {
                              C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'a3d_anytime_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'a3d_anytime_eval_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'a3d_binary_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
+                                  C.c_void_p]),
+    'a3d_counts_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_void_p]),
     'a3d_counts': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
                              C.c_void_p]),
     'a3d_pack_targets': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

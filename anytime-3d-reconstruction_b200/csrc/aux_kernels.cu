@@ -135,6 +135,67 @@ counts_kernel(const float* __restrict__ target, const float* __restrict__ pred, 
   }
 }
 
+// binary_loss (function.py:73-82, b_range = False): loss[b] = -sum_v gamma*y*log(p) + (1-gamma)*(1-y)*log(1-p),
+// p = clip(pred, 1e-7, 1-1e-7) in fp32.  grid = (chunks, B).
+__global__ void __launch_bounds__(256)
+binary_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t V, float gamma,
+                   double* __restrict__ loss) {
+  const int64_t b = blockIdx.y;
+  const float4* t4 = reinterpret_cast<const float4*>(target + b * V);
+  const float4* p4 = reinterpret_cast<const float4*>(pred + b * V);
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < V / 4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 t = __ldg(t4 + i), p = __ldg(p4 + i);
+    const float tv[4] = {t.x, t.y, t.z, t.w}, pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pc = fminf(fmaxf(pv[e], 1e-7f), 1.f - 1e-7f);
+      acc -= gamma * tv[e] * logf(pc) + (1.f - gamma) * (1.f - tv[e]) * logf(1.f - pc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss + b, (double)acc);
+}
+
+// Threshold sweep (modelnetAE3.ipynb cell 2): counts[b][t] += {TP, FP, FN} for T <= 32 thresholds.
+struct SweepThr { float v[32]; };
+__global__ void __launch_bounds__(256)
+counts_sweep_kernel(const float* __restrict__ target, const float* __restrict__ pred, int64_t V, SweepThr thr, int T,
+                    int strict, unsigned long long* __restrict__ counts) {
+  const int64_t b = blockIdx.y;
+  const float4* t4 = reinterpret_cast<const float4*>(target + b * V);
+  const float4* p4 = reinterpret_cast<const float4*>(pred + b * V);
+  __shared__ int red[32][3];
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) red[i / 3][i % 3] = 0;
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const float th = thr.v[t];
+    int tp = 0, fp = 0, fn = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < V / 4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 tt = __ldg(t4 + i), pp = __ldg(p4 + i);   // re-read per threshold: the chunk stays in L1/L2
+      const float tv[4] = {tt.x, tt.y, tt.z, tt.w}, pv[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int y = strict ? (pv[e] > th) : (pv[e] >= th), g = tv[e] > 0.5f;
+        tp += g & y;
+        fp += (1 - g) & y;
+        fn += g & (1 - y);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tp += __shfl_xor_sync(0xffffffffu, tp, o);
+      fp += __shfl_xor_sync(0xffffffffu, fp, o);
+      fn += __shfl_xor_sync(0xffffffffu, fn, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[t][0], tp); atomicAdd(&red[t][1], fp); atomicAdd(&red[t][2], fn); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * 3; i += blockDim.x)
+    if (red[i / 3][i % 3]) atomicAdd(counts + (b * T + i / 3) * 3 + i % 3, (unsigned long long)red[i / 3][i % 3]);
+}
+
 // bits[i] packs voxels 8i..8i+7 (bit e = voxel 8i + e).  total = B*V/8 bytes.
 __global__ void pack_kernel(const float* __restrict__ target, int64_t total_bytes, uint8_t* __restrict__ bits) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_bytes;
@@ -166,6 +227,30 @@ int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, 
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, (unsigned)B);
   counts_kernel<<<grid, 256, 0, st>>>(target, pred, V, thr, counts);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+int launch_binary_loss(const float* pred, const float* target, int64_t B, int64_t V, float gamma, double* loss,
+                       cudaStream_t st, int64_t* launches) {
+  if (B <= 0) return A3D_OK;
+  int chunks = (int)((V / 4 + 256 * 8 - 1) / (256 * 8));
+  if (chunks < 1) chunks = 1;
+  binary_loss_kernel<<<dim3(chunks, (unsigned)B), 256, 0, st>>>(pred, target, V, gamma, loss);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
+
+int launch_counts_sweep(const float* target, const float* pred, int64_t B, int64_t V, const float* thr, int T, int strict,
+                        unsigned long long* counts, cudaStream_t st, int64_t* launches) {
+  if (B <= 0 || T <= 0) return A3D_OK;
+  SweepThr tv;
+  for (int i = 0; i < 32; ++i) tv.v[i] = i < T ? thr[i] : 0.f;
+  int chunks = (int)((V / 4 + 256 * 8 - 1) / (256 * 8));
+  if (chunks < 1) chunks = 1;
+  counts_sweep_kernel<<<dim3(chunks, (unsigned)B), 256, 0, st>>>(target, pred, V, tv, T, strict, counts);
   A3D_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
   return A3D_OK;

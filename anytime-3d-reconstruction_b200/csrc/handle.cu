@@ -408,12 +408,13 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
 }
 
 int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, unsigned long long* counts, float* mean,
-             cudaStream_t st) {
+             float gamma, double* loss, cudaStream_t st) {
   const int sig = h->desc.final_activation == A3D_FINAL_SIGMOID;
   if (h->desc.impl == A3D_IMPL_SIMT)
-    return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, st, &h->launches);
-  return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, h->num_sms, st,
-                        &h->launches);
+    return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss, st,
+                       &h->launches);
+  return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss,
+                        h->num_sms, st, &h->launches);
 }
 
 void collect_profile(a3d_handle* h, cudaStream_t st, bool first) {
@@ -565,7 +566,7 @@ int a3d_decode(a3d_handle* h, const float* z_dev, int64_t n, float* prob_dev, vo
   for (int64_t off = 0; off < n; off += h->max_chunk) {
     const int64_t nc = (n - off < h->max_chunk) ? n - off : h->max_chunk;
     if ((rc = sticky(h, run_hidden(h, z_dev + off * D, nc, st)))) return rc;
-    rc = run_tail(h, nc, 1, nullptr, 0.5f, nullptr, prob_dev + off * (int64_t)A3D_VOXELS, st);
+    rc = run_tail(h, nc, 1, nullptr, 0.5f, nullptr, prob_dev + off * (int64_t)A3D_VOXELS, 0.f, nullptr, st);
     if ((rc = sticky(h, rc))) return rc;
     collect_profile(h, st, off == 0);
   }
@@ -586,11 +587,12 @@ int a3d_impute(a3d_handle* h, const float* z_dev, const float* mask_dev, const f
                                  z_out_dev, cstar_out_dev, (cudaStream_t)stream, &h->launches));
 }
 
-int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev, float thr,
-                     int64_t* counts_dev, float* mean_prob_dev, void* stream) {
+static int anytime_eval_impl(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev,
+                             float thr, float gamma, int64_t* counts_dev, double* loss_dev, float* mean_prob_dev,
+                             void* stream) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if (B < 0 || K < 1 || (B > 0 && !z_bkd_dev) || (target_bits_dev && !counts_dev)) {
+  if (B < 0 || K < 1 || (B > 0 && !z_bkd_dev) || (target_bits_dev && !counts_dev) || (loss_dev && !target_bits_dev)) {
     set_error("a3d_anytime_eval: bad arguments");
     return A3D_ERR_INVALID;
   }
@@ -603,17 +605,58 @@ int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, co
   cudaStream_t st = (cudaStream_t)stream;
   const int D = h->desc.latent_dim;
   if (counts_dev && B > 0) A3D_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)B * 3 * sizeof(int64_t), st));
+  if (loss_dev && B > 0) A3D_CUDA_OK(cudaMemsetAsync(loss_dev, 0, (size_t)B * sizeof(double), st));
   const int64_t obj_per_chunk = h->max_chunk / K;
   for (int64_t b0 = 0; b0 < B; b0 += obj_per_chunk) {
     const int64_t nb = (B - b0 < obj_per_chunk) ? B - b0 : obj_per_chunk;
     if ((rc = sticky(h, run_hidden(h, z_bkd_dev + b0 * K * D, nb * K, st)))) return rc;
     rc = run_tail(h, nb, K, target_bits_dev ? target_bits_dev + b0 * (A3D_VOXELS / 8) : nullptr, thr,
                   counts_dev ? reinterpret_cast<unsigned long long*>(counts_dev) + b0 * 3 : nullptr,
-                  mean_prob_dev ? mean_prob_dev + b0 * (int64_t)A3D_VOXELS : nullptr, st);
+                  mean_prob_dev ? mean_prob_dev + b0 * (int64_t)A3D_VOXELS : nullptr, gamma,
+                  loss_dev ? loss_dev + b0 : nullptr, st);
     if ((rc = sticky(h, rc))) return rc;
     collect_profile(h, st, b0 == 0);
   }
   return A3D_OK;
+}
+
+int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev, float thr,
+                     int64_t* counts_dev, float* mean_prob_dev, void* stream) {
+  return anytime_eval_impl(h, z_bkd_dev, B, K, target_bits_dev, thr, 0.f, counts_dev, nullptr, mean_prob_dev, stream);
+}
+
+int a3d_anytime_eval_loss(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev,
+                          float thr, float gamma, int64_t* counts_dev, double* loss_dev, float* mean_prob_dev,
+                          void* stream) {
+  return anytime_eval_impl(h, z_bkd_dev, B, K, target_bits_dev, thr, gamma, counts_dev, loss_dev, mean_prob_dev, stream);
+}
+
+int a3d_binary_loss(a3d_handle* h, const float* pred_dev, const float* target_dev, int64_t B, int64_t V, float gamma,
+                    double* loss_dev, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (B < 0 || V <= 0 || V % 4 != 0 || (B > 0 && (!pred_dev || !target_dev || !loss_dev))) {
+    set_error("a3d_binary_loss: bad arguments (V must be a positive multiple of 4)");
+    return A3D_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0) A3D_CUDA_OK(cudaMemsetAsync(loss_dev, 0, (size_t)B * sizeof(double), st));
+  return sticky(h, launch_binary_loss(pred_dev, target_dev, B, V, gamma, loss_dev, st, &h->launches));
+}
+
+int a3d_counts_sweep(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V,
+                     const float* thresholds, int T, int strict, int64_t* counts_dev, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (B < 0 || V <= 0 || V % 4 != 0 || T < 1 || T > 32 || !thresholds ||
+      (B > 0 && (!target_dev || !pred_dev || !counts_dev))) {
+    set_error("a3d_counts_sweep: bad arguments (1 <= T <= 32, V a positive multiple of 4)");
+    return A3D_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B > 0) A3D_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)B * T * 3 * sizeof(int64_t), st));
+  return sticky(h, launch_counts_sweep(target_dev, pred_dev, B, V, thresholds, T, strict,
+                                       reinterpret_cast<unsigned long long*>(counts_dev), st, &h->launches));
 }
 
 int a3d_counts(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V, float thr,

@@ -54,11 +54,15 @@ int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t 
                          cudaStream_t st, int64_t* launches);
 // Final ConvT(64->1, s2) + sigmoid + mean over K + threshold + TP/FP/FN (+ optional mean grid).
 int launch_tail(const void* a4, const float* w5, int64_t B, int K, int fmt, int final_sigmoid,
-                const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob,
-                cudaStream_t st, int64_t* launches);
+                const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob, float gamma,
+                double* loss, cudaStream_t st, int64_t* launches);
 int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64_t B, int K, int fmt,
                    int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                   float* mean_prob, int num_sms, cudaStream_t st, int64_t* launches);
+                   float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches);
+int launch_binary_loss(const float* pred, const float* target, int64_t B, int64_t V, float gamma, double* loss,
+                       cudaStream_t st, int64_t* launches);
+int launch_counts_sweep(const float* target, const float* pred, int64_t B, int64_t V, const float* thr, int T, int strict,
+                        unsigned long long* counts, cudaStream_t st, int64_t* launches);
 int launch_impute(const float* z, const float* mask, const float* mu, int C, int64_t B, int K, int D, uint64_t seed,
                   uint64_t obj_offset, int fill, float* z_out, int32_t* cstar, cudaStream_t st, int64_t* launches);
 int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, float thr,

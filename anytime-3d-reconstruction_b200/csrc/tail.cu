@@ -22,7 +22,8 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 tail_simt_kernel(const uint16_t* __restrict__ a4, const float* __restrict__ w5 /*[64 taps][64 ci]*/, int K,
                  int final_sigmoid, const uint8_t* __restrict__ target_bits, float thr,
-                 unsigned long long* __restrict__ counts, float* __restrict__ mean_prob) {
+                 unsigned long long* __restrict__ counts, float* __restrict__ mean_prob, float gamma,
+                 double* __restrict__ loss) {
   __shared__ float ws[64 * C4];
   for (int i = threadIdx.x; i < 64 * C4; i += blockDim.x) ws[i] = w5[i];
   __syncthreads();
@@ -80,6 +81,7 @@ tail_simt_kernel(const uint16_t* __restrict__ a4, const float* __restrict__ w5 /
 
   const float invk = 1.f / (float)K;
   int tp = 0, fp = 0, fn = 0;
+  float lsum = 0.f;
 #pragma unroll
   for (int p = 0; p < 8; p += 2) {
     const int pd = p >> 2, ph = (p >> 1) & 1;
@@ -94,9 +96,19 @@ tail_simt_kernel(const uint16_t* __restrict__ a4, const float* __restrict__ w5 /
       tp += (t0 & y0) + (t1 & y1);
       fp += ((1 - t0) & y0) + ((1 - t1) & y1);
       fn += (t0 & (1 - y0)) + (t1 & (1 - y1));
+      if (loss) {
+        const float c0 = fminf(fmaxf(m0, 1e-7f), 1.f - 1e-7f), c1 = fminf(fmaxf(m1, 1e-7f), 1.f - 1e-7f);
+        lsum -= t0 ? gamma * logf(c0) : (1.f - gamma) * logf(1.f - c0);
+        lsum -= t1 ? gamma * logf(c1) : (1.f - gamma) * logf(1.f - c1);
+      }
     }
   }
   if (target_bits) {
+    if (loss) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(loss + b, (double)lsum);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       tp += __shfl_xor_sync(0xffffffffu, tp, o);
@@ -114,16 +126,16 @@ tail_simt_kernel(const uint16_t* __restrict__ a4, const float* __restrict__ w5 /
 }  // namespace
 
 int launch_tail(const void* a4, const float* w5, int64_t B, int K, int fmt, int final_sigmoid,
-                const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob, cudaStream_t st,
-                int64_t* launches) {
+                const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob, float gamma,
+                double* loss, cudaStream_t st, int64_t* launches) {
   if (B <= 0) return A3D_OK;
   dim3 grid(G4 * G4 * G4 / 256, (unsigned)B);
   if (fmt == A3D_DTYPE_F16)
     tail_simt_kernel<A3D_DTYPE_F16><<<grid, 256, 0, st>>>((const uint16_t*)a4, w5, K, final_sigmoid, target_bits, thr,
-                                                         counts, mean_prob);
+                                                         counts, mean_prob, gamma, loss);
   else
     tail_simt_kernel<A3D_DTYPE_BF16><<<grid, 256, 0, st>>>((const uint16_t*)a4, w5, K, final_sigmoid, target_bits, thr,
-                                                          counts, mean_prob);
+                                                          counts, mean_prob, gamma, loss);
   A3D_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
   return A3D_OK;

@@ -43,7 +43,8 @@ template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
                int K, int final_sigmoid, const uint8_t* __restrict__ target_bits, float thr,
-               unsigned long long* __restrict__ counts, float* __restrict__ mean_prob) {
+               unsigned long long* __restrict__ counts, float* __restrict__ mean_prob, float gamma,
+               double* __restrict__ loss) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle, computed on the shared-window address so the pointer keeps its
   // __shared__ provenance (LDS/STS instead of generic LD/ST)
@@ -210,6 +211,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
       }
       // ---- finalize the block: mean over K, threshold, compare with the target bits
       int tp = 0, fp = 0, fn = 0;
+      float lsum = 0.f;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
@@ -226,9 +228,18 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           tp += t & yv;
           fp += (1 - t) & yv;
           fn += t & (1 - yv);
+          if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
+            const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
+            lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
+          }
         }
       }
       if (target_bits) {
+        if (loss) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+          if (lane == 0) atomicAdd(loss + b, (double)lsum);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           tp += __shfl_xor_sync(0xffffffffu, tp, o);
@@ -253,13 +264,14 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
 
 int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64_t B, int K, int fmt,
                    int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                   float* mean_prob, int num_sms, cudaStream_t st, int64_t* launches) {
+                   float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches) {
   if (B <= 0) return A3D_OK;
   const int64_t items = B * kItemsPerObj;
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4, tmap_w5, B, K, final_sigmoid, target_bits, thr, counts, mean_prob);
+    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4, tmap_w5, B, K, final_sigmoid, target_bits, thr, counts, mean_prob, gamma,
+                                        loss);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };

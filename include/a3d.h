@@ -93,6 +93,23 @@ int a3d_impute(a3d_handle* h, const float* z_dev, const float* mask_dev, const f
 int a3d_anytime_eval(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev,
                      float thr, int64_t* counts_dev, float* mean_prob_dev, void* stream);
 
+/* a3d_anytime_eval plus the weighted-BCE shape loss the reference's getEval reports next to the counts:
+ * binary_loss(xPred, xTarget, gamma)   src/module/function.py:73-82, called with gamma = 0.60 at src/module/nolbo.py:1497,1521.
+ * loss_dev: [B] double = -sum_v (gamma*y*log(p) + (1-gamma)*(1-y)*log(1-p)), p = clip(mean grid, 1e-7, 1-1e-7); overwritten. */
+int a3d_anytime_eval_loss(a3d_handle* h, const float* z_bkd_dev, int64_t B, int K, const uint8_t* target_bits_dev,
+                          float thr, float gamma, int64_t* counts_dev, double* loss_dev, float* mean_prob_dev,
+                          void* stream);
+
+/* binary_loss(xPred, xTarget, epsilon = 1e-7, gamma)   src/module/function.py:73-82 (b_range = False), stand-alone form on
+ * fp32 grids [B, V]; loss_dev [B] double. */
+int a3d_binary_loss(a3d_handle* h, const float* pred_dev, const float* target_dev, int64_t B, int64_t V, float gamma,
+                    double* loss_dev, void* stream);
+
+/* Precision/recall threshold sweep of the evaluation notebooks (modelnetAE3.ipynb cell 2): for each of T thresholds
+ * yPred = strict ? (xPred > thr) : (xPred >= thr); counts_dev [B, T, 3] int64 (TP, FP, FN).  thresholds: host, T <= 32. */
+int a3d_counts_sweep(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V,
+                     const float* thresholds, int T, int strict, int64_t* counts_dev, void* stream);
+
 /* voxelPrecisionRecall(xTarget, xPred, prob)   src/module/function.py:100-115.  Both [B, V] fp32 on the device;
  * counts_dev [B, 3] int64 = TP, FP, FN with yPred = (xPred >= thr), yTarget = (xTarget > 0.5). */
 int a3d_counts(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V, float thr,

@@ -164,6 +164,30 @@ def counts(x_target: np.ndarray, x_pred: np.ndarray, prob: float = 0.5) -> np.nd
     return np.stack([tp, fp, fn], -1).astype(np.int64)
 
 
+def binary_loss(x_pred: np.ndarray, x_target: np.ndarray, gamma: float = 0.5, epsilon: float = 1e-7) -> np.ndarray:
+    """function.py:73-82 with b_range = False: -sum_v gamma*y*log(p) + (1-gamma)*(1-y)*log(1-p), p clipped in fp32
+    like tf.clip_by_value; the sum is evaluated in fp64.  Returns [B]."""
+    b = x_pred.shape[0]
+    p = np.clip(np.asarray(x_pred, np.float32).reshape(b, -1), np.float32(epsilon), np.float32(1.0) - np.float32(epsilon))
+    y = np.asarray(x_target, np.float64).reshape(b, -1)
+    p = p.astype(np.float64)
+    return -(gamma * y * np.log(p) + (1.0 - gamma) * (1.0 - y) * np.log(1.0 - p)).sum(-1)
+
+
+def counts_sweep(x_target: np.ndarray, x_pred: np.ndarray, thresholds, strict: bool = True) -> np.ndarray:
+    """modelnetAE3.ipynb cell 2: yPred = (xPred > prob) per threshold -> [B, T, 3] int64."""
+    b = x_target.shape[0]
+    yt = np.asarray(x_target).reshape(b, -1) > 0.5
+    xp = np.asarray(x_pred, np.float32).reshape(b, -1)
+    out = np.zeros((b, len(thresholds), 3), np.int64)
+    for i, th in enumerate(np.asarray(thresholds, np.float32)):
+        yp = xp > th if strict else xp >= th
+        out[:, i, 0] = (yt & yp).sum(-1)
+        out[:, i, 1] = (~yt & yp).sum(-1)
+        out[:, i, 2] = (yt & ~yp).sum(-1)
+    return out
+
+
 def iou_from_counts(c: np.ndarray):
     """IoU = TP / (TP+FP+FN) (derived; the reference reports pr/rc from the same counts, nolbo.py:1499-1501).
     Returns (mean over objects of per-object IoU, global sum-then-ratio IoU)."""

@@ -200,6 +200,25 @@ def test_voxel_precision_recall_exact(a3d_mod):
     assert np.array_equal(pack_targets(d, t).cpu().numpy(), ar.pack_bits(t))
 
 
+def test_binary_loss_and_threshold_sweep(a3d_mod):
+    rng = np.random.default_rng(12)
+    B = 3
+    t = (rng.random((B, 64, 64, 64, 1)) < 0.15).astype(np.float32)
+    p = rng.random((B, 64, 64, 64, 1)).astype(np.float32)
+    p[0].reshape(-1)[:500] = 0.0          # clipped to 1e-7
+    p[1].reshape(-1)[:500] = 1.0          # clipped to 1 - 1e-7
+    got = a3d_mod.binary_loss(p, t, gamma=0.6)
+    ref = ar.binary_loss(p, t, gamma=0.6)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        a3d_mod.binary_loss(p, t, b_range=True)
+    thr = [(i + 1) / 20 for i in range(19)]                     # notebook: r2 with div = 20
+    c = a3d_mod.voxelPrecisionRecallSweep(t, p, thr)
+    assert np.array_equal(c, ar.counts_sweep(t, p, thr, strict=True))
+    c2 = a3d_mod.voxelPrecisionRecallSweep(t, p, [0.5], strict=False)
+    assert np.array_equal(c2[:, 0], ar.counts(t, p, 0.5))
+
+
 # ------------------------------------------------------------------------------------------------ fused anytime path
 def test_anytime_eval_golden(a3d_mod, decoders, golden):
     dec = decoders[('mn', 'trained')]
@@ -237,6 +256,11 @@ def test_anytime_eval_vs_oracle(a3d_mod, weights, B, K, chunk, fill):
     # exact invariants of the counts: TP + FN = target occupancy, TP + FP = predicted occupancy
     assert np.array_equal(cnt[:, 0] + cnt[:, 2], tgt.reshape(B, -1).sum(1).astype(np.int64))
     assert np.array_equal(cnt[:, 0] + cnt[:, 1], (mp.reshape(B, -1) >= 0.5).sum(1))
+    # fused weighted-BCE loss: exact arithmetic check on the GPU's own mean grid, and close to the oracle's loss
+    rl = a3d_mod.anytime_eval(dec, z, mask, mu, tgt, K=K, seed=77, fill=fill, return_loss=True, gamma=0.6)
+    assert torch.equal(rl['counts'], r['counts'])
+    np.testing.assert_allclose(rl['loss'].cpu().numpy(), ar.binary_loss(mp, tgt, gamma=0.6), rtol=1e-5)
+    np.testing.assert_allclose(rl['loss'].cpu().numpy(), ar.binary_loss(ref_mp, tgt, gamma=0.6), rtol=2e-2)
     # counts-only call (no grid) and host-buffer call give the same integers
     r2 = a3d_mod.anytime_eval(dec, z, mask, mu, ar.pack_bits(tgt), K=K, seed=77, fill=fill)
     assert torch.equal(r2['counts'], r['counts'])
@@ -269,8 +293,9 @@ def test_getEval_reference_return_tuple(a3d_mod, decoders):
     cat = np.eye(40, dtype=np.float32)[rng.integers(0, 40, B)]
     out = a3d_mod.getEval(dec, (z, tgt, cat), mu, missing_prob=0.0)
     assert len(out) == 10 and out[5:] == (0, 0, 0, 0, 0) and tuple(out[0].shape) == (B, 64, 64, 64, 1)
+    assert out[1] == pytest.approx(float(ar.binary_loss(out[0].cpu().numpy(), tgt, gamma=0.6).mean()), rel=1e-5)
     out = a3d_mod.getEval(dec, (z, tgt, cat), mu, missing_prob=0.5, K=4, seed=1, rng=np.random.default_rng(0))
-    assert len(out) == 10 and tuple(out[5].shape) == (B, 64, 64, 64, 1) and 0.0 <= out[7] <= 1.0
+    assert len(out) == 10 and tuple(out[5].shape) == (B, 64, 64, 64, 1) and 0.0 <= out[7] <= 1.0 and out[6] > 0
 
 
 def test_full_size_properties_config2(a3d_mod, weights):
