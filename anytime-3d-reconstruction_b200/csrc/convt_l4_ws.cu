@@ -262,7 +262,7 @@ convt_l4_ws_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             const int wr = grow / NT, nr = nb * NT + grow % NT;
             if (nr < n_alloc) {
               const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
-              *reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8) = val;
+              __stcs(reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8), val);   // streaming: keep L2 for the inputs
             }
           }
           __syncwarp();

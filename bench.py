@@ -279,10 +279,20 @@ def main():
     decodes_per_launch = B_PER_RATE * K
     tpeak, hpeak, src = peaks()
     l4_tflops = 2.0 * L4_MACS * decodes_per_launch / (stage['l4'] * 1e-3) / 1e12
-    roofline = {'bound': 'tensor', 'kernel': 'convt_l4_ws_kernel (128->64 ConvT, 2-CTA weight-stationary)', 'achieved': l4_tflops, 'peak': tpeak,
-                'unit': 'TFLOP/s', 'frac': l4_tflops / tpeak, 'traffic': None, 'peak_source': f'{src} sustained bf16',
-                'stage_ms': stage,
-                'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12}
+    # algorithmic bytes of the fused tail per launch (SURVEY 8d variant B): K * 4 MiB of bf16/fp16 activations + target
+    # bits + counts per object
+    tail_bytes = B_PER_RATE * (K * 2_097_152 * 2 + 262_144 // 8 + 24)
+    tail_gbs = tail_bytes / (stage['tail'] * 1e-3) / 1e9
+    roofline = {'bound': 'tensor', 'kernel': 'convt_l4_ws_kernel (128->64 ConvT, 2-CTA weight-stationary)',
+                'achieved': l4_tflops, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': l4_tflops / tpeak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this size, from the
+                # ncu --set full capture committed as profiles/r01_l4_ws2cta_ncu_full.txt (algorithmic: 21.5e9)
+                'traffic': 30.17e9, 'traffic_unit': 'bytes per launch (ncu, profiles/r01_l4_ws2cta_ncu_full.txt)',
+                'peak_source': f'{src} sustained bf16', 'stage_ms': stage,
+                'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12,
+                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_tc_kernel (final ConvT + sigmoid + K-mean + threshold + counts)',
+                               'achieved': tail_gbs, 'peak': hpeak, 'unit': 'GB/s', 'frac': tail_gbs / hpeak,
+                               'traffic': 17.70e9, 'algorithmic_bytes_per_launch': tail_bytes}}
 
     if rank == 0:
         cpu = None
