@@ -325,3 +325,59 @@ def test_full_size_properties_config2(a3d_mod, weights):
     tg = np.unpackbits(bits[[3, 200]], axis=1, bitorder='little').reshape(2, 64, 64, 64, 1)
     _, ref_cnt = ar.anytime_eval(dr.MODELNET_DECODER, ws, zc, tg)
     assert np.abs(cnt[[3, 200]] - ref_cnt).sum() <= 2 * FLIP_TOL * 262144 * 2
+
+
+def test_prefix_sweep_properties_config4(a3d_mod, decoders):
+    """BASELINE config 4 semantics on a small batch: prefix masks; the full prefix reproduces the plain decode and the
+    sharded run (object offset) reproduces the slice of the unsharded one bit-for-bit."""
+    dec = decoders[('mn', 'trained')]
+    rng = np.random.default_rng(31)
+    B = 6
+    z = dr.round_bf16(rng.standard_normal((B, 64)).astype(np.float32))
+    mu = rng.standard_normal((40, 64)).astype(np.float32)
+    tgt = ar.make_targets(rng, B)
+    lengths = [1, 16, 32, 64]
+    zz = np.repeat(z, len(lengths), axis=0)
+    mask = np.tile(ar.prefix_mask(len(lengths), 64, lengths), (B, 1))
+    bits = np.repeat(ar.pack_bits(tgt), len(lengths), axis=0)
+    r = a3d_mod.anytime_eval(dec, zz, mask, mu, bits, K=1, seed=4, return_grid=True)
+    zc = r['z_completed'].cpu().numpy()
+    assert np.array_equal(zc[3::4, 0], z)                       # prefix 64 = nothing imputed
+    full = dec(z)
+    assert np.array_equal(r['mean_prob'].cpu().numpy()[3::4], full)
+    assert np.array_equal(zc[0::4, 0, :1], z[:, :1]) and not np.array_equal(zc[0::4, 0, 1:], z[:, 1:])
+    part = a3d_mod.anytime_eval(dec, zz[8:], mask[8:], mu, bits[8:], K=1, seed=4, obj_offset=8)
+    assert torch.equal(part['counts'], r['counts'][8:])
+
+
+def test_pascal_path_config3(a3d_mod, decoders, weights):
+    """BASELINE config 3 decoder path: D = 16 latents drawn with sampling(mean, logvar), decoded and scored."""
+    dec, ws = decoders[('pa', 'trained')], weights[('pa', 'trained')]
+    rng = np.random.default_rng(32)
+    B = 7
+    mean = rng.standard_normal((B, 16)).astype(np.float32)
+    logvar = np.clip(rng.standard_normal((B, 16)).astype(np.float32) - 2.0, -10, 10)
+    z = a3d_mod.sampling(mean, logvar, seed=9, decoder=dec)
+    eps = ar.philox_normals(9, np.arange(B, dtype=np.uint64), 1, 16)[:, 0]
+    assert np.abs(z - ar.sampling(mean, logvar, eps)).max() < 2e-5
+    tgt = ar.make_targets(rng, B)
+    r = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=z[:, None, :], return_grid=True)
+    ref_mp, ref_cnt = ar.anytime_eval(dr.PASCAL_DECODER, ws, z[:, None, :], tgt)
+    mp = r['mean_prob'].cpu().numpy()
+    nflip = int(((mp >= 0.5) != (ref_mp >= 0.5)).sum())
+    assert np.abs(mp - ref_mp).max() < PROB_TOL and nflip / mp.size < FLIP_TOL
+    assert np.abs(r['counts'].cpu().numpy() - ref_cnt).sum() <= 2 * nflip
+
+
+@pytest.mark.parametrize('n', [1, 8, 9, 31, 33])
+def test_ragged_decode_sizes_match_simt_path(a3d_mod, weights, n):
+    """Every tile-size boundary of the tcgen05 kernels (8 / 16 / 32 / 128 decodes per tile, CTA pairs) against the
+    CUDA-core diagnostic path on the same device."""
+    ws = weights[('mn', 'trained')]
+    z = np.random.default_rng(n).standard_normal((n, 64)).astype(np.float32)
+    t = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=64)
+    s = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=64, impl='simt')
+    t.set_weights(ws)
+    s.set_weights(ws)
+    a, b = t(z), s(z)
+    assert np.isfinite(a).all() and np.abs(a - b).max() < 5e-3 and flips(a, b) < 2e-4
