@@ -7,6 +7,7 @@ Host-side mirror of the reference interface for this path (same names, argument 
 * ``model.set_weights / get_weights / load_weights / save_weights``  <- nolbo.py:1568-1592 (Keras variable order)
 * ``sampling(mu, logVar)``                 <- src/module/function.py:35-38
 * ``voxelPrecisionRecall(xTarget, xPred, prob)``  <- src/module/function.py:100-115
+* ``Darknet19(...)`` / ``head2D(...)``     <- src/net_core/darknet.py:96-133,149-168 (image encoder, encoder2d.py)
 * ``anytime_eval(...)`` / ``getEval(...)`` <- the imputation + decode + score sequence of nolbo.py:1449-1528 with the
   K-sample mean of nolbo_test.py:167-177
 
@@ -26,10 +27,11 @@ import numpy as np
 
 from . import _capi, presets
 from ._capi import FILL, VOXELS
+from .encoder2d import Darknet19, Encoder2D, head2D, image_encoder
 
 __all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'voxelPrecisionRecallSweep', 'binary_loss',
            'anytime_eval', 'anytime_eval_host', 'impute', 'getEval', 'pack_targets', 'iou_from_counts', 'shard_range',
-           'allreduce_counts']
+           'allreduce_counts', 'Darknet19', 'head2D', 'image_encoder', 'Encoder2D', 'getEvalImages']
 
 
 def _torch():
@@ -491,6 +493,21 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
         return pred, loss, pr, rc, acc, 0, 0, 0, 0, 0   # :1502-1503
     pred_c, loss_c, pr_c, rc_c, acc_c = branch('prior_sample', K)
     return pred, loss, pr, rc, acc, pred_c, loss_c, pr_c, rc_c, acc_c
+
+
+def getEvalImages(encoder: Encoder2D, decoder: Decoder3D, inputs, category_vectors, training: bool = False,
+                  missing_prob: float = 0.0, K: int = 1, seed: int = 0, mask=None,
+                  rng: np.random.Generator | None = None):
+    """``nolboSingleObject_pascal_category_VAE.getEval`` (nolbo.py:855-935) end to end: ``inputs = (input_images,
+    output_images, category_list)`` with RGB crops [B,H,W,3] in [0,1]; the encoder (Darknet19 + head2D, one handle from
+    ``image_encoder``) produces mean / clipped logvar / z on the GPU (nolbo.py:869-875), then the latent-space
+    ``getEval`` above runs unchanged.  Returns the same 10-tuple."""
+    if training:
+        raise NotImplementedError('inference only')
+    input_images, output_images, category_list = inputs
+    _, _, z = encoder.encode(input_images, decoder.input_dim, seed=seed ^ 0x656E63)
+    return getEval(decoder, (z, output_images, category_list), category_vectors, missing_prob=missing_prob, K=K,
+                   seed=seed, mask=mask, rng=rng)
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU plumbing

@@ -11,6 +11,11 @@ A3D_MAX_LAYERS = 8
 VOXELS = 262144
 
 ACT = {'None': 0, None: 0, 'linear': 0, 'elu': 1, 'relu': 2, 'lrelu': 3}
+# darknet.py:87-92 / :140-145: 'lrelu' there is LeakyReLU(alpha=0.1)
+ACT2D = {'None': 0, None: 0, 'linear': 0, 'elu': 1, 'relu': 2, 'lrelu': 4}
+A3D_ENC_MAX_LAYERS = 40
+L2D = {'conv': 0, 'maxpool': 1, 'global_max': 2, 'global_avg': 3}
+IO = {'fp16': 0, 'f16': 0, 'float16': 0, 'bf16': 1, 'bfloat16': 1, 'fp32': 2, 'f32': 2, 'float32': 2}
 FINAL = {'None': 0, None: 0, 'linear': 0, 'sigmoid': 1}
 DTYPE = {'fp16': 0, 'f16': 0, 'float16': 0, 'bf16': 1, 'bfloat16': 1}
 IMPL = {'tcgen05': 0, 'simt': 1}
@@ -25,6 +30,17 @@ class Desc(C.Structure):
         ('final_activation', C.c_int32), ('device', C.c_int32), ('max_chunk', C.c_int32),
         ('operand_dtype', C.c_int32), ('impl', C.c_int32),
     ]
+
+
+class Layer2d(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('filters', C.c_int32), ('ksize', C.c_int32), ('batch_norm', C.c_int32),
+                ('activation', C.c_int32)]
+
+
+class Enc2dDesc(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('in_ch', C.c_int32),
+                ('num_layers', C.c_int32), ('layers', Layer2d * A3D_ENC_MAX_LAYERS), ('device', C.c_int32),
+                ('max_batch', C.c_int32), ('operand_dtype', C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/a3d.h declares (tests check this against the header)
@@ -57,6 +73,20 @@ SIGNATURES = {
     'a3d_launch_count': (C.c_int64, [C.c_void_p]),
     'a3d_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'a3d_stage_times_ms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    'a3d_enc2d_create': (C.c_int, [C.POINTER(Enc2dDesc), C.POINTER(C.c_void_p)]),
+    'a3d_enc2d_destroy': (None, [C.c_void_p]),
+    'a3d_enc2d_num_weights': (C.c_int, [C.c_void_p]),
+    'a3d_enc2d_weight_numel': (C.c_int64, [C.c_void_p, C.c_int]),
+    'a3d_enc2d_set_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'a3d_enc2d_get_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'a3d_enc2d_output_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    'a3d_enc2d_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    'a3d_enc2d_split_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int,
+                                         C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'a3d_enc2d_layer_shape': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    'a3d_enc2d_debug_read_layer': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]),
+    'a3d_enc2d_launch_count': (C.c_int64, [C.c_void_p]),
+    'a3d_enc2d_workspace_bytes': (C.c_size_t, [C.c_void_p]),
     'a3d_last_error': (C.c_char_p, []),
     'a3d_abi_version': (C.c_int, []),
 }

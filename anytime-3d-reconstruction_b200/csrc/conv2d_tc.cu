@@ -1,0 +1,301 @@
+// Stride-1 'same' Conv2D (k = 1 or 3, no bias) + folded BatchNorm + activation as a tcgen05 implicit GEMM
+// (Darknet19Conv / convHead / the final head conv, src/net_core/darknet.py:83-94,135-147,155-157).
+//
+//   D[p, co] = sum_{dy,dx,ci} X[n, h+dy-1, w+dx-1, ci] * W[dy, dx, ci, co]        p = (n, h, w) flattened, NHWC
+//
+// M tile = a brick of wt x ht pixels x nt images (wt * ht * nt = 128, powers of two; the encoder's grids are powers of
+// two), N tile = BN output channels, K = taps x Cin in chunks of 64 channels.  A operand: one 4-D TMA box
+// (64 ch, wt, ht, nt) of the (c, w, h, n) view per (tap, chunk), started at (w0+dx-1, h0+dy-1): the out-of-bounds zero
+// fill of TMA *is* the 'same' padding, per image.  B operand: 2-D TMA box (64 ci, BN rows) of the weights repacked to
+// [tap][co][ci].  fp32 accumulators double-buffered in TMEM, so the BN + activation epilogue of unit i overlaps the
+// main loop of unit i+1; persistent CTAs, units ordered n-tile fastest so the CTAs that share an activation tile run
+// at the same time (L2 reuse).
+//
+// POOL = true fuses the MaxPool2D(2, 2) that follows the convolution (darknet.py:100,104,110,116,124): the brick is
+// then at most 16 pixels wide, so the 2 x 2 partners of a pixel sit in lanes (lane ^ 1) and (lane ^ wt) of the same
+// epilogue warp: two shuffles + packed max per register pair, and each lane of the quad stores one 16-byte quarter of
+// the pooled 64-byte segment.  max() runs on the rounded 16-bit values (rounding is monotonic, so this equals
+// rounding after the pool).
+#include <cstdlib>
+
+#include "epilogue.cuh"
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace a3d {
+namespace {
+
+constexpr int BM = 128;
+constexpr int A_BYTES = BM * 128;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + NUM_BARS * 8 + 16;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float act2d(float v) {
+  if constexpr (ACT == A3D_ACT_LRELU01) return v > 0.f ? v : 0.1f * v;
+  else return activate<ACT>(v);
+}
+
+__device__ __forceinline__ uint32_t max2_f16(uint32_t a, uint32_t b) {
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t max2_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// MODE 0: 16-bit [pixels, cout_pad]; 1: fp32 [pixels, cout_real] (final head conv; feeds the global pool);
+// 2: 16-bit with the 2 x 2 max-pool fused, [n, H/2, W/2, cout_pad]
+template <int BN, int FMT, int ACT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
+                 void* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
+                 Conv2dGeom g) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::STAGES * C::B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* t_full = empty + C::STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = g.m_tiles * g.n_tiles;
+  const int ksteps = g.taps * g.cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_act);
+    ptx::prefetch_tmap(&tmap_wgt);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kEpiWarps); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_slot, 512);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===================================================== TMA producer
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int nt = u % g.n_tiles, mt = u / g.n_tiles;
+        const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
+        const int w0 = tw << g.lw, h0 = th << g.lh, n0 = nb << (7 - g.lw - g.lh);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dx = g.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < g.cin_chunks; ++kc, ++it) {
+            const int s = it % C::STAGES;
+            ptx::mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+            ptx::mbar_expect_tx(&full[s], A_BYTES + C::B_BYTES);
+            tma_load_4d(smem_a + s * A_BYTES, &tmap_act, &full[s], kc * 64, w0 + dx, h0 + dy, n0);
+            ptx::tma_load_2d(smem_b + s * C::B_BYTES, &tmap_wgt, &full[s], kc * 64, tap * g.cout_pad + nt * BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (converged warp, elected-lane issue)
+    constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN, FMT);
+    const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
+    const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
+    uint32_t it = 0, unit_it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+      const int buf = unit_it & 1;
+      ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * BN;
+      for (int ks = 0; ks < ksteps; ++ks, ++it) {
+        const int s = it % C::STAGES;
+        ptx::mbar_wait(&full[s], (it / C::STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4), b_lo = b_lo0 + s * (C::B_BYTES >> 4);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + kk * 2), ptx::sw128_desc(b_lo + kk * 2), idesc,
+                             (ks | kk) != 0);
+          ptx::umma_commit<1>(&empty[s]);
+          if (ks == ksteps - 1) ptx::umma_commit<1>(&t_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: TMEM -> BN -> act -> global (direct 16 B stores)
+    const int e = warp - 4;
+    const int quarter = e & 3, chalf = e >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    constexpr int GROUPS = BN / 2 / 32;   // 32-column groups per warp
+    uint32_t unit_it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
+      const int nt = u % g.n_tiles, mt = u / g.n_tiles;
+      const int buf = unit_it & 1;
+      ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + lane_base + buf * BN + chalf * (BN / 2);
+      const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
+      const int r = quarter * 32 + lane;
+      const int wi = r & ((1 << g.lw) - 1), hi = (r >> g.lw) & ((1 << g.lh) - 1), ni = r >> (g.lw + g.lh);
+      const int img = (nb << (7 - g.lw - g.lh)) + ni;
+      const int ph = (th << g.lh) + hi, pw = (tw << g.lw) + wi;
+      const bool row_ok = img < g.n_images;
+      const int64_t p = MODE == 2 ? ((int64_t)img * (g.H >> 1) + (ph >> 1)) * (g.W >> 1) + (pw >> 1)
+                                  : ((int64_t)img * g.H + ph) * g.W + pw;
+#pragma unroll 1
+      for (int gi = 0; gi < GROUPS; ++gi) {
+        const int co0 = nt * BN + chalf * (BN / 2) + gi * 32;
+        uint32_t v[32];
+        ptx::tmem_ld16(tacc + gi * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        ptx::tmem_ld16(tacc + gi * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        ptx::tmem_ld_wait();
+        const float4* sc4 = reinterpret_cast<const float4*>(scale + co0);
+        const float4* sh4 = reinterpret_cast<const float4*>(shift + co0);
+        if constexpr (MODE == 1) {
+          float* dst = reinterpret_cast<float*>(out) + p * g.cout_real + co0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);
+            float x[4];
+            x[0] = act2d<ACT>(fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x));
+            x[1] = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y));
+            x[2] = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z));
+            x[3] = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w));
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (co0 + 4 * i + j < g.cout_real) dst[4 * i + j] = x[j];
+            }
+          }
+        } else {
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);
+            const float x0 = act2d<ACT>(fmaf(__uint_as_float(v[4 * i]), sc.x, sh.x));
+            const float x1 = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 1]), sc.y, sh.y));
+            const float x2 = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 2]), sc.z, sh.z));
+            const float x3 = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w));
+            o[2 * i] = pack2<FMT>(x0, x1);
+            o[2 * i + 1] = pack2<FMT>(x2, x3);
+          }
+          if constexpr (MODE == 2) {
+            const int wt = 1 << g.lw;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              uint32_t t = __shfl_xor_sync(0xffffffffu, o[i], 1);
+              o[i] = FMT == A3D_DTYPE_F16 ? max2_f16(o[i], t) : max2_bf16(o[i], t);
+              t = __shfl_xor_sync(0xffffffffu, o[i], wt);
+              o[i] = FMT == A3D_DTYPE_F16 ? max2_f16(o[i], t) : max2_bf16(o[i], t);
+            }
+            const int sub = (wi & 1) | ((hi & 1) << 1);
+            uint4 q;
+            q.x = sub == 0 ? o[0] : sub == 1 ? o[4] : sub == 2 ? o[8] : o[12];
+            q.y = sub == 0 ? o[1] : sub == 1 ? o[5] : sub == 2 ? o[9] : o[13];
+            q.z = sub == 0 ? o[2] : sub == 1 ? o[6] : sub == 2 ? o[10] : o[14];
+            q.w = sub == 0 ? o[3] : sub == 1 ? o[7] : sub == 2 ? o[11] : o[15];
+            if (row_ok)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0 + sub * 8) = q;
+          } else if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int BN, int FMT, int MODE>
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const float* scale, const float* shift,
+              const Conv2dGeom& g, int act, int grid, cudaStream_t st) {
+  auto launch = [&](auto kern) -> int {
+    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
+    A3D_CUDA_OK(cudaGetLastError());
+    return A3D_OK;
+  };
+  switch (act) {
+    case A3D_ACT_ELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_ELU, MODE>);
+    case A3D_ACT_RELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_RELU, MODE>);
+    case A3D_ACT_LRELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_LRELU, MODE>);
+    case A3D_ACT_LRELU01: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_LRELU01, MODE>);
+    case A3D_ACT_NONE: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_NONE, MODE>);
+    default: set_error("conv2d: unsupported activation %d", act); return A3D_ERR_INVALID;
+  }
+}
+
+template <int BN>
+int launch_fmt(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const float* scale, const float* shift,
+               const Conv2dGeom& g, int fmt, int act, int mode, int grid, cudaStream_t st) {
+  if (fmt == A3D_DTYPE_F16) {
+    if (mode == 0) return launch_bn<BN, A3D_DTYPE_F16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
+    if (mode == 1) return launch_bn<BN, A3D_DTYPE_F16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
+    return launch_bn<BN, A3D_DTYPE_F16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
+  }
+  if (mode == 0) return launch_bn<BN, A3D_DTYPE_BF16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
+  if (mode == 1) return launch_bn<BN, A3D_DTYPE_BF16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
+  return launch_bn<BN, A3D_DTYPE_BF16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
+}
+
+}  // namespace
+
+int conv2d_tc_bn(int cout_pad) { return cout_pad % 256 == 0 ? 256 : (cout_pad % 128 == 0 ? 128 : 64); }
+
+int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
+                     const float* shift, const Conv2dGeom& g, int bn, int fmt, int act, bool pool, bool out_f32,
+                     int num_sms, cudaStream_t st, int64_t* launches) {
+  if (g.n_images <= 0) return A3D_OK;
+  if (pool && (out_f32 || g.lw > 4 || g.lh < 1 || (g.H & 1) || (g.W & 1))) {
+    set_error("conv2d: fused pool needs a brick at most 16 wide and at least 2 high on even sizes");
+    return A3D_ERR_INVALID;
+  }
+  const int total = g.m_tiles * g.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  const int mode = out_f32 ? 1 : (pool ? 2 : 0);
+  int rc;
+  if (bn == 256) rc = launch_fmt<256>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  else if (bn == 128) rc = launch_fmt<128>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  else rc = launch_fmt<64>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  if (rc == A3D_OK && launches) ++*launches;
+  return rc;
+}
+
+}  // namespace a3d

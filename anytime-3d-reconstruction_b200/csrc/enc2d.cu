@@ -1,0 +1,471 @@
+// Host side of the image encoder (a3d_enc2d_* entry points of include/a3d.h): Darknet19 backbone + head2D of the
+// Pascal3D path, src/net_core/darknet.py:83-168, called as head(backbone(images)) at src/module/nolbo.py:869.
+// Owns the Keras-order weights, folds BatchNorm, repacks the Conv2D kernels to [tap][co][ci] 16-bit rows, builds the TMA
+// tensor maps once and drives the per-chunk launch sequence on the caller's stream.
+//
+// Execution plan: a conv followed by a max-pool becomes ONE launch (pool fused into the epilogue); the 3-channel first
+// layer runs on CUDA cores (K = 27); every other conv is a tcgen05 implicit GEMM; a final conv followed by a global
+// pool writes fp32 and a small reduction kernel produces [n, C].  All hidden activations are 16-bit NHWC with the
+// channel count padded to a multiple of 64 (pad channels are zero: zero weights rows/scale 0/shift 0).
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+
+using namespace a3d;
+
+namespace {
+
+enum { OP_FIRST = 0, OP_CONV = 1, OP_POOL = 2, OP_GPOOL = 3 };
+
+struct Op2d {
+  int kind = 0;
+  int layer = 0;              // index into the layer list of the layer whose output this op produces
+  int H = 0, W = 0;           // input spatial size
+  int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, ksize = 0, act = 0;
+  bool bn = false, pool = false, out_f32 = false, is_max = false;
+  int in_buf = -1, out_buf = -1;
+  int w_index = -1;           // index of the kernel variable in the Keras weight list
+  int bn_tile = 0;
+  Conv2dGeom g;
+  CUtensorMap tmap_act, tmap_wgt;
+  void* wgt = nullptr;        // device: 16-bit [tap][cout_pad][cin_pad], or fp32 [27][32] (first layer)
+  float *scale = nullptr, *shift = nullptr;
+};
+
+struct Buf2d {
+  int H = 0, W = 0, C = 0, C_pad = 0;
+  bool f32 = false;
+  int64_t alloc_n = 0;
+  void* ptr = nullptr;
+};
+
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct a3d_enc2d {
+  a3d_enc2d_desc desc{};
+  int num_sms = 0;
+  std::vector<Op2d> ops;
+  std::vector<Buf2d> bufs;          // bufs[0] = imported input (feature-map models only)
+  std::vector<int> layer_buf;       // layer index -> buffer holding its output (pooled for conv+pool pairs)
+  std::vector<std::vector<float>> w;
+  std::vector<int64_t> w_numel;
+  std::vector<bool> w_set;
+  bool dirty = true;
+  int out_h = 0, out_w = 0, out_c = 0;
+  bool out_is_pooled_f32 = false;
+  int final_buf = -1;
+  size_t arena_bytes = 0;
+  int64_t launches = 0;
+  int64_t last_n = 0;
+  int sticky = 0;
+};
+
+namespace {
+
+int check(const a3d_enc2d* h) {
+  if (!h) { set_error("null encoder handle"); return A3D_ERR_INVALID; }
+  if (h->sticky) { set_error("encoder handle is in a sticky CUDA error state (%d)", h->sticky); return h->sticky; }
+  return A3D_OK;
+}
+int sticky(a3d_enc2d* h, int rc) {
+  if (rc == A3D_ERR_CUDA) h->sticky = rc;
+  return rc;
+}
+
+// brick of the conv M tile: contiguous pixels for plain convs, at most 16 wide (and >= 2 high) when a pool is fused
+void choose_brick(Op2d& op) {
+  const int W = op.W, H = op.H;
+  int wt = op.pool ? (W < 16 ? W : 16) : (W < 128 ? W : 128);
+  int ht = 128 / wt;
+  if (ht > H) ht = H;
+  Conv2dGeom& g = op.g;
+  g.H = H; g.W = W;
+  g.lw = ilog2(wt); g.lh = ilog2(ht);
+  g.tiles_w = W / wt; g.tiles_h = H / ht;
+  g.taps = op.ksize * op.ksize;
+  g.cin_chunks = op.cin_pad / 64;
+  g.cout_pad = op.cout_pad;
+  g.cout_real = op.cout;
+  g.n_tiles = op.cout_pad / op.bn_tile;
+}
+
+int build_plan(a3d_enc2d* h) {
+  const a3d_enc2d_desc& d = h->desc;
+  int H = d.in_h, W = d.in_w, C = d.in_ch;
+  int cur = -1;     // buffer holding the current activation; -1 = the user's fp32 image
+  int C_pad = C;
+  h->layer_buf.assign(d.num_layers, -1);
+  if (C % 64 == 0) {
+    Buf2d b; b.H = H; b.W = W; b.C = C; b.C_pad = C;
+    h->bufs.push_back(b);
+    cur = 0;
+  } else if (C != 3) {
+    set_error("in_ch must be 3 (images) or a multiple of 64 (feature maps), got %d", C);
+    return A3D_ERR_INVALID;
+  }
+  int w_index = 0;
+  for (int li = 0; li < d.num_layers; ++li) {
+    const a3d_layer2d& L = d.layers[li];
+    const bool next_pool = li + 1 < d.num_layers && d.layers[li + 1].kind == A3D_L2D_MAXPOOL;
+    const bool next_gpool = li + 1 < d.num_layers && (d.layers[li + 1].kind == A3D_L2D_GLOBAL_MAX ||
+                                                      d.layers[li + 1].kind == A3D_L2D_GLOBAL_AVG);
+    if (L.kind == A3D_L2D_CONV) {
+      if ((L.ksize != 1 && L.ksize != 3) || L.filters < 1 || L.activation < 0 || L.activation > A3D_ACT_LRELU01) {
+        set_error("layer %d: Conv2D needs ksize 1 or 3, filters >= 1 and a known activation", li);
+        return A3D_ERR_INVALID;
+      }
+      Op2d op;
+      op.layer = li; op.H = H; op.W = W; op.cin = C; op.cin_pad = C_pad; op.cout = L.filters;
+      op.cout_pad = round_up(L.filters, 64); op.ksize = L.ksize; op.act = L.activation; op.bn = L.batch_norm != 0;
+      op.in_buf = cur; op.w_index = w_index;
+      h->w_numel.push_back((int64_t)L.ksize * L.ksize * C * L.filters);
+      if (op.bn) for (int i = 0; i < 4; ++i) h->w_numel.push_back(L.filters);
+      w_index += op.bn ? 5 : 1;
+      if (cur < 0) {
+        // the 3-channel image layer: CUDA-core kernel with the following pool fused (darknet.py:99-100)
+        if (L.ksize != 3 || L.filters != 32 || !next_pool || (H & 1) || (W & 1)) {
+          set_error("layer %d: the image layer must be Conv2D(32, 3) followed by MaxPool2D(2,2) (Darknet19)", li);
+          return A3D_ERR_INVALID;
+        }
+        op.kind = OP_FIRST; op.pool = true;
+      } else {
+        op.kind = OP_CONV;
+        op.pool = next_pool;
+        op.out_f32 = next_gpool;
+        if (op.pool && ((H & 1) || (W & 1))) { set_error("layer %d: max-pool on an odd size", li); return A3D_ERR_INVALID; }
+        op.bn_tile = conv2d_tc_bn(op.cout_pad);
+        choose_brick(op);
+        if (op.pool && op.g.lh < 1) { set_error("layer %d: fused pool needs H >= 2", li); return A3D_ERR_INVALID; }
+      }
+      Buf2d b;
+      b.H = op.pool ? H / 2 : H; b.W = op.pool ? W / 2 : W; b.C = L.filters;
+      b.C_pad = op.out_f32 ? L.filters : op.cout_pad; b.f32 = op.out_f32;
+      h->bufs.push_back(b);
+      op.out_buf = (int)h->bufs.size() - 1;
+      h->ops.push_back(op);
+      cur = op.out_buf;
+      h->layer_buf[li] = cur;
+      H = b.H; W = b.W; C = L.filters; C_pad = b.C_pad;
+      if (op.pool) { h->layer_buf[li + 1] = cur; ++li; }
+    } else if (L.kind == A3D_L2D_MAXPOOL) {
+      if (cur < 0 || (H & 1) || (W & 1) || h->bufs[cur].f32) { set_error("layer %d: unsupported MaxPool2D placement", li); return A3D_ERR_INVALID; }
+      Op2d op;
+      op.kind = OP_POOL; op.layer = li; op.H = H; op.W = W; op.cin = C; op.cin_pad = C_pad; op.cout = C; op.cout_pad = C_pad;
+      op.in_buf = cur;
+      Buf2d b; b.H = H / 2; b.W = W / 2; b.C = C; b.C_pad = C_pad;
+      h->bufs.push_back(b);
+      op.out_buf = (int)h->bufs.size() - 1;
+      h->ops.push_back(op);
+      cur = op.out_buf; h->layer_buf[li] = cur; H /= 2; W /= 2;
+    } else if (L.kind == A3D_L2D_GLOBAL_MAX || L.kind == A3D_L2D_GLOBAL_AVG) {
+      if (cur < 0 || !h->bufs[cur].f32 || li != d.num_layers - 1) {
+        set_error("layer %d: a global pool must be the last layer and directly follow a Conv2D (head2D)", li);
+        return A3D_ERR_INVALID;
+      }
+      Op2d op;
+      op.kind = OP_GPOOL; op.layer = li; op.H = H; op.W = W; op.cin = C; op.cout = C; op.is_max = L.kind == A3D_L2D_GLOBAL_MAX;
+      op.in_buf = cur; op.out_buf = -1;   // writes the caller's buffer
+      h->ops.push_back(op);
+      h->layer_buf[li] = -1;
+      H = 1; W = 1;
+      h->out_is_pooled_f32 = true;
+    } else {
+      set_error("layer %d: unknown kind %d", li, L.kind);
+      return A3D_ERR_INVALID;
+    }
+  }
+  if (h->ops.empty()) { set_error("empty layer list"); return A3D_ERR_INVALID; }
+  h->out_h = H; h->out_w = W; h->out_c = C;
+  h->final_buf = cur;
+  if (!h->out_is_pooled_f32 && h->bufs[cur].f32) { set_error("internal: fp32 final buffer without a global pool"); return A3D_ERR_INVALID; }
+  h->w.assign(h->w_numel.size(), {});
+  h->w_set.assign(h->w_numel.size(), false);
+  return A3D_OK;
+}
+
+int alloc_arena(a3d_enc2d* h) {
+  // each buffer holds max_batch images rounded up to the image count of its consumer's GEMM brick (TMA boxes stay
+  // inside the allocation; rows past the real batch are never stored)
+  for (auto& b : h->bufs) b.alloc_n = h->desc.max_batch;
+  for (auto& op : h->ops)
+    if (op.kind == OP_CONV) {
+      const int nt = 128 >> (op.g.lw + op.g.lh);
+      Buf2d& b = h->bufs[op.in_buf];
+      const int64_t need = (int64_t)round_up(h->desc.max_batch, nt);
+      if (need > b.alloc_n) b.alloc_n = need;
+    }
+  for (auto& b : h->bufs) {
+    const size_t bytes = (size_t)b.alloc_n * b.H * b.W * b.C_pad * (b.f32 ? 4 : 2);
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) { set_error("encoder arena allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return A3D_ERR_CUDA; }
+    A3D_CUDA_OK(cudaMemset(b.ptr, 0, bytes));
+    h->arena_bytes += bytes;
+  }
+  return A3D_OK;
+}
+
+int make_maps(a3d_enc2d* h, Op2d& op) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return A3D_ERR_CUDA; }
+  const CUtensorMapDataType dt =
+      h->desc.operand_dtype == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const Buf2d& b = h->bufs[op.in_buf];
+  const uint64_t C = op.cin_pad, W = op.W, H = op.H;
+  cuuint64_t dims[4] = {C, W, H, (cuuint64_t)b.alloc_n};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, 1u << op.g.lw, 1u << op.g.lh, 128u >> (op.g.lw + op.g.lh)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(&op.tmap_act, dt, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder activations, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
+  cuuint64_t wd[2] = {C, (cuuint64_t)op.ksize * op.ksize * op.cout_pad};
+  cuuint64_t ws[1] = {C * 2};
+  cuuint32_t wb[2] = {64, (cuuint32_t)op.bn_tile};
+  r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder weights, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
+  return A3D_OK;
+}
+
+int finalize(a3d_enc2d* h) {
+  if (!h->dirty) return A3D_OK;
+  for (size_t i = 0; i < h->w_set.size(); ++i)
+    if (!h->w_set[i]) { set_error("encoder weight %zu of %zu was never set", i, h->w_set.size()); return A3D_ERR_WEIGHTS; }
+  const int fmt = h->desc.operand_dtype;
+  int rc;
+  std::vector<float> sc, sf;
+  std::vector<uint16_t> p16;
+  for (auto& op : h->ops) {
+    if (op.kind != OP_FIRST && op.kind != OP_CONV) continue;
+    const std::vector<float>& k = h->w[op.w_index];     // Keras Conv2D kernel [kh][kw][cin][cout]
+    if (op.bn) fold_bn(h->w[op.w_index + 1], h->w[op.w_index + 2], h->w[op.w_index + 3], h->w[op.w_index + 4], sc, sf);
+    else { sc.assign(op.cout, 1.f); sf.assign(op.cout, 0.f); }
+    sc.resize(op.cout_pad, 0.f);     // pad channels: scale 0, shift 0 -> act(0) = 0 for every supported activation
+    sf.resize(op.cout_pad, 0.f);
+    if ((rc = upload(sc.data(), sc.size() * 4, (void**)&op.scale))) return rc;
+    if ((rc = upload(sf.data(), sf.size() * 4, (void**)&op.shift))) return rc;
+    const int taps = op.ksize * op.ksize;
+    if (op.kind == OP_FIRST) {
+      if ((rc = upload(k.data(), k.size() * 4, &op.wgt))) return rc;   // already [tap][ci][co] = [27][32]
+    } else {
+      p16.assign((size_t)taps * op.cout_pad * op.cin_pad, cvt16(0.f, fmt));
+      for (int t = 0; t < taps; ++t)
+        for (int ci = 0; ci < op.cin; ++ci) {
+          const float* src = &k[((size_t)t * op.cin + ci) * op.cout];
+          for (int co = 0; co < op.cout; ++co)
+            p16[((size_t)t * op.cout_pad + co) * op.cin_pad + ci] = cvt16(src[co], fmt);
+        }
+      if ((rc = upload(p16.data(), p16.size() * 2, &op.wgt))) return rc;
+      if ((rc = make_maps(h, op))) return rc;
+    }
+  }
+  h->dirty = false;
+  return A3D_OK;
+}
+
+int run_chunk(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* out_dev, int out_dtype, cudaStream_t st) {
+  const int fmt = h->desc.operand_dtype;
+  int rc;
+  if (h->desc.in_ch % 64 == 0) {
+    const Buf2d& b = h->bufs[0];
+    if ((rc = launch_import_nhwc(in_dev, in_dtype == A3D_IO_F32, b.ptr, n * b.H * b.W, b.C, b.C_pad, fmt, st, &h->launches)))
+      return rc;
+  }
+  for (auto& op : h->ops) {
+    void* out = op.out_buf >= 0 ? h->bufs[op.out_buf].ptr : out_dev;
+    switch (op.kind) {
+      case OP_FIRST:
+        rc = launch_conv2d_first_pool(reinterpret_cast<const float*>(in_dev), reinterpret_cast<const float*>(op.wgt),
+                                      op.scale, op.shift, out, n, op.H, op.W, op.cout_pad, fmt, op.act, st, &h->launches);
+        break;
+      case OP_CONV: {
+        Conv2dGeom g = op.g;
+        const int nt = 128 >> (g.lw + g.lh);
+        g.n_images = (int)n;
+        g.m_tiles = (int)((n + nt - 1) / nt) * g.tiles_w * g.tiles_h;
+        rc = launch_conv2d_tc(op.tmap_act, op.tmap_wgt, out, op.scale, op.shift, g, op.bn_tile, fmt, op.act, op.pool,
+                              op.out_f32, h->num_sms, st, &h->launches);
+        break;
+      }
+      case OP_POOL:
+        rc = launch_maxpool2d(h->bufs[op.in_buf].ptr, out, n, op.H, op.W, op.cin_pad, fmt, st, &h->launches);
+        break;
+      case OP_GPOOL:
+        rc = launch_global_pool(reinterpret_cast<const float*>(h->bufs[op.in_buf].ptr), reinterpret_cast<float*>(out_dev),
+                                n, op.H * op.W, op.cin, op.is_max ? 1 : 0, st, &h->launches);
+        break;
+      default: rc = A3D_ERR_INVALID;
+    }
+    if (rc) return rc;
+  }
+  if (!h->out_is_pooled_f32) {
+    const Buf2d& b = h->bufs[h->final_buf];
+    if ((rc = launch_export_nhwc(b.ptr, out_dev, out_dtype == A3D_IO_F32, n * b.H * b.W, b.C, b.C_pad, fmt, st, &h->launches)))
+      return rc;
+  }
+  h->last_n = n;
+  return A3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int a3d_enc2d_create(const a3d_enc2d_desc* d, a3d_enc2d** out) {
+  if (!d || !out) { set_error("null argument"); return A3D_ERR_INVALID; }
+  *out = nullptr;
+  if (d->abi_version != A3D_ABI_VERSION) { set_error("ABI version mismatch: %d vs %d", d->abi_version, A3D_ABI_VERSION); return A3D_ERR_INVALID; }
+  if (d->num_layers < 1 || d->num_layers > A3D_ENC_MAX_LAYERS) { set_error("num_layers must be in [1, %d]", A3D_ENC_MAX_LAYERS); return A3D_ERR_INVALID; }
+  if (!is_pow2(d->in_h) || !is_pow2(d->in_w)) {
+    set_error("in_h / in_w must be powers of two (got %d x %d); the reference evaluates 256 x 256 crops", d->in_h, d->in_w);
+    return A3D_ERR_INVALID;
+  }
+  if (d->operand_dtype != A3D_DTYPE_F16 && d->operand_dtype != A3D_DTYPE_BF16) { set_error("invalid operand dtype"); return A3D_ERR_INVALID; }
+  if (d->max_batch < 1) { set_error("max_batch must be >= 1"); return A3D_ERR_INVALID; }
+  a3d_enc2d* h = new a3d_enc2d();
+  h->desc = *d;
+  int rc = build_plan(h);   // validates the structure before any device work (usable without a GPU for error paths)
+  if (rc) { delete h; return rc; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device >= ndev) {
+    cudaGetLastError();
+    set_error("no CUDA device %d available; liba3d has no CPU path", d->device);
+    delete h;
+    return A3D_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess || prop.major != 10) {
+    set_error("device %d is not sm_100; liba3d is built for sm_100a only", d->device);
+    delete h;
+    return A3D_ERR_NO_DEVICE;
+  }
+  cudaSetDevice(d->device);
+  h->num_sms = prop.multiProcessorCount;
+  if ((rc = alloc_arena(h))) { a3d_enc2d_destroy(h); return rc; }
+  *out = h;
+  return A3D_OK;
+}
+
+void a3d_enc2d_destroy(a3d_enc2d* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (auto& b : h->bufs) cudaFree(b.ptr);
+  for (auto& op : h->ops) { cudaFree(op.wgt); cudaFree(op.scale); cudaFree(op.shift); }
+  delete h;
+}
+
+int a3d_enc2d_num_weights(const a3d_enc2d* h) { return h ? (int)h->w_numel.size() : 0; }
+int64_t a3d_enc2d_weight_numel(const a3d_enc2d* h, int index) {
+  return (h && index >= 0 && index < (int)h->w_numel.size()) ? h->w_numel[index] : -1;
+}
+
+int a3d_enc2d_set_weight(a3d_enc2d* h, int index, const float* host, size_t nbytes) {
+  int rc = check(h);
+  if (rc) return rc;
+  if (index < 0 || index >= (int)h->w_numel.size() || !host) { set_error("bad encoder weight index %d", index); return A3D_ERR_INVALID; }
+  if (nbytes != (size_t)h->w_numel[index] * 4) {
+    set_error("encoder weight %d: expected %lld fp32 values, got %zu bytes", index, (long long)h->w_numel[index], nbytes);
+    return A3D_ERR_WEIGHTS;
+  }
+  h->w[index].assign(host, host + h->w_numel[index]);
+  h->w_set[index] = true;
+  h->dirty = true;
+  return A3D_OK;
+}
+
+int a3d_enc2d_get_weight(const a3d_enc2d* h, int index, float* host, size_t nbytes) {
+  if (!h || index < 0 || index >= (int)h->w_numel.size() || !host) { set_error("bad encoder weight index %d", index); return A3D_ERR_INVALID; }
+  if (!h->w_set[index]) { set_error("encoder weight %d was never set", index); return A3D_ERR_WEIGHTS; }
+  if (nbytes != (size_t)h->w_numel[index] * 4) { set_error("encoder weight %d: size mismatch", index); return A3D_ERR_WEIGHTS; }
+  memcpy(host, h->w[index].data(), nbytes);
+  return A3D_OK;
+}
+
+int a3d_enc2d_output_shape(const a3d_enc2d* h, int32_t* out_dims) {
+  if (!h || !out_dims) { set_error("null argument"); return A3D_ERR_INVALID; }
+  out_dims[0] = h->out_h; out_dims[1] = h->out_w; out_dims[2] = h->out_c;
+  return A3D_OK;
+}
+
+int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* out_dev, int out_dtype,
+                      void* stream) {
+  int rc = check(h);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!in_dev || !out_dev))) { set_error("a3d_enc2d_forward: bad arguments"); return A3D_ERR_INVALID; }
+  const bool image_in = h->desc.in_ch == 3;
+  if ((image_in && in_dtype != A3D_IO_F32) || (!image_in && in_dtype != A3D_IO_F32 && in_dtype != h->desc.operand_dtype)) {
+    set_error("a3d_enc2d_forward: input must be fp32%s", image_in ? " (images)" : " or the handle's operand dtype");
+    return A3D_ERR_INVALID;
+  }
+  if ((h->out_is_pooled_f32 && out_dtype != A3D_IO_F32) || (out_dtype != A3D_IO_F32 && out_dtype != h->desc.operand_dtype)) {
+    set_error("a3d_enc2d_forward: output must be fp32%s", h->out_is_pooled_f32 ? " (global pool)" : " or the handle's operand dtype");
+    return A3D_ERR_INVALID;
+  }
+  if ((rc = sticky(h, finalize(h)))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t in_es = in_dtype == A3D_IO_F32 ? 4 : 2, out_es = out_dtype == A3D_IO_F32 ? 4 : 2;
+  const size_t in_per = (size_t)h->desc.in_h * h->desc.in_w * h->desc.in_ch * in_es;
+  const size_t out_per = (size_t)h->out_h * h->out_w * h->out_c * out_es;
+  for (int64_t off = 0; off < n; off += h->desc.max_batch) {
+    const int64_t nc = n - off < h->desc.max_batch ? n - off : h->desc.max_batch;
+    rc = run_chunk(h, reinterpret_cast<const uint8_t*>(in_dev) + off * in_per, in_dtype, nc,
+                   reinterpret_cast<uint8_t*>(out_dev) + off * out_per, out_dtype, st);
+    if ((rc = sticky(h, rc))) return rc;
+  }
+  return A3D_OK;
+}
+
+int a3d_enc2d_split_sample(a3d_enc2d* h, const float* enc_out_dev, int64_t n, int D, int out_stride, float clip,
+                           int seed_enable, uint64_t seed, uint64_t obj_offset, float* mean_dev, float* logvar_dev,
+                           float* z_dev, void* stream) {
+  int rc = check(h);
+  if (rc) return rc;
+  if (n < 0 || D < 1 || out_stride < 2 * D || (n > 0 && !enc_out_dev)) { set_error("a3d_enc2d_split_sample: bad arguments"); return A3D_ERR_INVALID; }
+  return sticky(h, launch_split_sample(enc_out_dev, n, D, out_stride, clip, seed_enable, seed, obj_offset, mean_dev,
+                                       logvar_dev, z_dev, (cudaStream_t)stream, &h->launches));
+}
+
+int a3d_enc2d_layer_shape(const a3d_enc2d* h, int layer, int32_t* dims) {
+  if (!h || !dims || layer < 0 || layer >= h->desc.num_layers) { set_error("bad layer index"); return A3D_ERR_INVALID; }
+  const int bi = h->layer_buf[layer];
+  if (bi < 0) { dims[0] = 1; dims[1] = 1; dims[2] = h->out_c; dims[3] = h->out_c; return A3D_OK; }
+  const Buf2d& b = h->bufs[bi];
+  dims[0] = b.H; dims[1] = b.W; dims[2] = b.C; dims[3] = b.C_pad;
+  return A3D_OK;
+}
+
+int a3d_enc2d_debug_read_layer(a3d_enc2d* h, int layer, int64_t n, float* host, size_t nbytes) {
+  int rc = check(h);
+  if (rc) return rc;
+  if (layer < 0 || layer >= h->desc.num_layers || h->layer_buf[layer] < 0 || n <= 0 || n > h->desc.max_batch || !host) {
+    set_error("a3d_enc2d_debug_read_layer: bad arguments");
+    return A3D_ERR_INVALID;
+  }
+  const Buf2d& b = h->bufs[h->layer_buf[layer]];
+  const size_t elems = (size_t)n * b.H * b.W * b.C_pad;
+  if (nbytes != elems * 4) { set_error("a3d_enc2d_debug_read_layer: expected %zu bytes", elems * 4); return A3D_ERR_INVALID; }
+  A3D_CUDA_OK(cudaDeviceSynchronize());
+  if (b.f32) {
+    A3D_CUDA_OK(cudaMemcpy(host, b.ptr, nbytes, cudaMemcpyDeviceToHost));
+    return A3D_OK;
+  }
+  float* tmp = nullptr;
+  A3D_CUDA_OK(cudaMalloc(&tmp, nbytes));
+  rc = launch_to_f32(b.ptr, tmp, (int64_t)elems, h->desc.operand_dtype, 0);
+  if (rc == A3D_OK) {
+    cudaError_t e = cudaMemcpy(host, tmp, nbytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("debug copy failed: %s", cudaGetErrorString(e)); rc = A3D_ERR_CUDA; }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+int64_t a3d_enc2d_launch_count(const a3d_enc2d* h) { return h ? h->launches : 0; }
+size_t a3d_enc2d_workspace_bytes(const a3d_enc2d* h) { return h ? h->arena_bytes : 0; }
+
+}  // extern "C"

@@ -26,13 +26,7 @@ void set_error(const char* fmt, ...) {
 
 using namespace a3d;
 
-namespace {
-
-constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default epsilon
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+namespace a3d {
 
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -59,7 +53,25 @@ uint16_t cvt16(float v, int fmt) {
   return r;
 }
 
-}  // namespace
+int upload(const void* src, size_t bytes, void** dst) {
+  if (!*dst) A3D_CUDA_OK(cudaMalloc(dst, bytes));
+  A3D_CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return A3D_OK;
+}
+
+void fold_bn(const std::vector<float>& g, const std::vector<float>& b, const std::vector<float>& m,
+             const std::vector<float>& v, std::vector<float>& scale, std::vector<float>& shift) {
+  const size_t n = g.size();
+  scale.resize(n);
+  shift.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float s = g[i] / std::sqrt(v[i] + kBnEps);
+    scale[i] = s;
+    shift[i] = b[i] - m[i] * s;
+  }
+}
+
+}  // namespace a3d
 
 struct a3d_handle {
   a3d_desc desc{};
@@ -129,24 +141,6 @@ void build_weight_table(a3d_handle* h) {
   h->n_weights = (int)h->w_numel.size();
   h->w.assign(h->n_weights, {});
   h->w_set.assign(h->n_weights, false);
-}
-
-int upload(const void* src, size_t bytes, void** dst) {
-  if (!*dst) A3D_CUDA_OK(cudaMalloc(dst, bytes));
-  A3D_CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
-  return A3D_OK;
-}
-
-void fold_bn(const std::vector<float>& g, const std::vector<float>& b, const std::vector<float>& m,
-             const std::vector<float>& v, std::vector<float>& scale, std::vector<float>& shift) {
-  const size_t n = g.size();
-  scale.resize(n);
-  shift.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    const float s = g[i] / std::sqrt(v[i] + kBnEps);
-    scale[i] = s;
-    shift[i] = b[i] - m[i] * s;
-  }
 }
 
 inline int tap_of(int p, int s) { return 3 - p - 2 * s; }  // tap = p + 1 - 2*delta, delta = s - 1 + p

@@ -22,6 +22,18 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default epsilon
+
+// host helpers shared by handle.cu (decoder) and enc2d.cu (image encoder)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+uint16_t cvt16(float v, int fmt);
+int upload(const void* src, size_t bytes, void** dst);   // cudaMalloc on first use + synchronous H2D copy
+void fold_bn(const std::vector<float>& g, const std::vector<float>& b, const std::vector<float>& m,
+             const std::vector<float>& v, std::vector<float>& scale, std::vector<float>& shift);
+
 // One stride-2 transposed-conv layer (k=4, 'same'): in [N, W,W,W, CIN] -> out [N, 2W,2W,2W, COUT], NDHWC, 16-bit.
 struct ConvLayer {
   int cin = 0, cout = 0, win = 0;
@@ -69,6 +81,39 @@ int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, 
                   unsigned long long* counts, cudaStream_t st, int64_t* launches);
 int launch_pack(const float* target, int64_t B, int64_t V, uint8_t* bits, cudaStream_t st, int64_t* launches);
 int launch_to_f32(const void* src, float* dst, int64_t n, int fmt, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-D image encoder (Darknet19 + head2D, src/net_core/darknet.py:83-168); kernels in conv2d_tc.cu / enc2d_kernels.cu
+// Geometry of one stride-1 'same' Conv2D launch.  The GEMM M tile is a brick of wt x ht pixels x nt images
+// (wt * ht * nt = 128, all powers of two) so that one 4-D TMA box per (tap, 64-channel chunk) fetches the A operand.
+struct Conv2dGeom {
+  int H = 0, W = 0;            // spatial size of the conv input (= output, stride 1)
+  int lw = 0, lh = 0;          // log2(wt), log2(ht); nt = 128 >> (lw + lh)
+  int tiles_w = 0, tiles_h = 0;
+  int m_tiles = 0, n_tiles = 0;
+  int taps = 0, cin_chunks = 0, cout_pad = 0, cout_real = 0;
+  int n_images = 0;
+};
+int conv2d_tc_bn(int cout_pad);
+// pool: fuse the MaxPool2D(2, 2) that follows (out = [n, H/2, W/2, cout_pad] 16-bit); out_f32: out = [n*H*W, cout_real] fp32
+int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
+                     const float* shift, const Conv2dGeom& g, int bn, int fmt, int act, bool pool, bool out_f32,
+                     int num_sms, cudaStream_t st, int64_t* launches);
+// first layer: Conv2D(3 -> 32, k3) + BN + act + MaxPool2D(2,2); in fp32 [n,H,W,3], out 16-bit [n,H/2,W/2,cout_pad]
+int launch_conv2d_first_pool(const float* in, const float* w27x32, const float* scale, const float* shift, void* out,
+                             int64_t n, int H, int W, int cout_pad, int fmt, int act, cudaStream_t st, int64_t* launches);
+int launch_maxpool2d(const void* in, void* out, int64_t n, int H, int W, int C, int fmt, cudaStream_t st,
+                     int64_t* launches);
+int launch_global_pool(const float* in, float* out, int64_t n, int HW, int C, int is_max, cudaStream_t st,
+                       int64_t* launches);
+// NHWC channel-(un)padding copies between user buffers (fp32 or 16-bit) and the 16-bit arena
+int launch_import_nhwc(const void* in, int in_is_f32, void* out, int64_t pixels, int C, int C_pad, int fmt,
+                       cudaStream_t st, int64_t* launches);
+int launch_export_nhwc(const void* in, void* out, int out_is_f32, int64_t pixels, int C, int C_pad, int fmt,
+                       cudaStream_t st, int64_t* launches);
+int launch_split_sample(const float* enc_out, int64_t n, int D, int out_stride, float clip, int seed_enable,
+                        uint64_t seed, uint64_t obj_offset, float* mean, float* logvar, float* z, cudaStream_t st,
+                        int64_t* launches);
 
 size_t convt_tc_smem_bytes(int cin, int cout, int win);
 

@@ -13,5 +13,12 @@ MODELNET_DECODER = {
 }
 # test_pascal_VAE_dr.py:196-205 (latent dim 16)
 PASCAL_DECODER = dict(MODELNET_DECODER, input_dim=16)
+# test_pascal_VAE_dr.py:186-195 (encoder backbone / head of the Pascal3D VAE; head built with last_pooling='max',
+# src/module/nolbo.py:778-783)
+PASCAL_ENCODER_BACKBONE = {'name': 'nolbo_backbone', 'z_dim': 16, 'activation': 'elu'}
+PASCAL_ENCODER_HEAD = {'name': 'nolbo_head', 'output_dim': 32, 'filter_num_list': [], 'filter_size_list': [],
+                       'activation': 'elu'}
+PASCAL_IMAGE_SIZE = (256, 256)   # test_pascal_VAE_dr.py:52
 
+FLOP_PER_IMAGE_ENCODER = 7.162e9   # 2 x 3.581 GMAC at 256 x 256, interior + border taps
 FLOP_PER_DECODE = {64: 6.663830528e9, 16: 6.663781376e9}  # exact MAC*2, SURVEY.md section 7

@@ -35,7 +35,8 @@ typedef enum {
   A3D_ERR_WORKSPACE = -5    /* request exceeds the arena             */
 } a3d_status;
 
-enum { A3D_ACT_NONE = 0, A3D_ACT_ELU = 1, A3D_ACT_RELU = 2, A3D_ACT_LRELU = 3 };
+enum { A3D_ACT_NONE = 0, A3D_ACT_ELU = 1, A3D_ACT_RELU = 2, A3D_ACT_LRELU = 3 /* slope 0.3 (Keras default) */,
+       A3D_ACT_LRELU01 = 4 /* LeakyReLU(alpha=0.1), src/net_core/darknet.py:88,141 */ };
 enum { A3D_FINAL_NONE = 0, A3D_FINAL_SIGMOID = 1 };
 enum { A3D_DTYPE_F16 = 0, A3D_DTYPE_BF16 = 1 };          /* operand type of the tensor-core layers */
 enum { A3D_IMPL_TCGEN05 = 0, A3D_IMPL_SIMT = 1 };        /* SIMT = CUDA-core kernels, bring-up/diagnostic only */
@@ -139,6 +140,79 @@ int64_t a3d_launch_count(const a3d_handle* h);
  * a3d_set_profiling(h, 1): stages = dense+L1, L2, L3, L4, tail.  Returns number of stages written. */
 int a3d_set_profiling(a3d_handle* h, int enable);
 int a3d_stage_times_ms(a3d_handle* h, float* out, int max_stages);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Image encoder of the Pascal3D path: Darknet19 backbone + head2D,
+ * src/net_core/darknet.py:83-133 (Darknet19Conv / Darknet19), :135-168 (convHead / head2D).  A handle holds one
+ * Keras-style functional model given as a flat layer list; the reference builds two models (backbone, head) and
+ * calls head(backbone(images)) (src/module/nolbo.py:869), so two handles chain through a 16-bit NHWC feature buffer,
+ * or one handle holds both lists concatenated.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define A3D_ENC_MAX_LAYERS 40
+enum { A3D_L2D_CONV = 0,         /* Conv2D(filters, ksize 1|3, strides 1, 'same', use_bias=False) [+ BN] [+ act] */
+       A3D_L2D_MAXPOOL = 1,      /* MaxPool2D(2, 2, 'same') on even sizes                                         */
+       A3D_L2D_GLOBAL_MAX = 2,   /* tf.reduce_max(axis=[1,2])   darknet.py:159-160                                */
+       A3D_L2D_GLOBAL_AVG = 3 }; /* tf.reduce_mean(axis=[1,2])  darknet.py:162-163                                */
+enum { A3D_IO_F16 = 0, A3D_IO_BF16 = 1, A3D_IO_F32 = 2 };   /* element type of a forward() input / output buffer */
+
+typedef struct {
+  int32_t kind;         /* A3D_L2D_*                                  */
+  int32_t filters;      /* conv only                                  */
+  int32_t ksize;        /* conv only: 1 or 3                          */
+  int32_t batch_norm;   /* conv only: BatchNormalization() follows    */
+  int32_t activation;   /* conv only: A3D_ACT_*                       */
+} a3d_layer2d;
+
+typedef struct {
+  int32_t abi_version;  /* A3D_ABI_VERSION */
+  int32_t in_h, in_w;   /* input height / width: powers of two (the reference runs 256 x 256, test_pascal_VAE_dr.py:52) */
+  int32_t in_ch;        /* 3 for images; a multiple of 64 for feature maps (head-only model) */
+  int32_t num_layers;
+  a3d_layer2d layers[A3D_ENC_MAX_LAYERS];
+  int32_t device;
+  int32_t max_batch;    /* images resident in the arena at once; larger calls are processed in chunks */
+  int32_t operand_dtype;/* A3D_DTYPE_* of the tensor-core layers */
+} a3d_enc2d_desc;
+
+typedef struct a3d_enc2d a3d_enc2d;
+
+/* Darknet19(name, activation) / head2D(name, input_shape, output_dim, ...) -> model     darknet.py:96-133,149-168 */
+int a3d_enc2d_create(const a3d_enc2d_desc* desc, a3d_enc2d** out);
+void a3d_enc2d_destroy(a3d_enc2d* h);
+
+/* Keras variables in model.get_weights() order: per conv layer kernel [kh,kw,Cin,Cout], then (if BN) gamma, beta,
+ * moving_mean, moving_variance.  fp32, host, synchronous; folding / repacking happens lazily before the next forward. */
+int a3d_enc2d_num_weights(const a3d_enc2d* h);
+int64_t a3d_enc2d_weight_numel(const a3d_enc2d* h, int index);
+int a3d_enc2d_set_weight(a3d_enc2d* h, int index, const float* host, size_t nbytes);
+int a3d_enc2d_get_weight(const a3d_enc2d* h, int index, float* host, size_t nbytes);
+
+/* Output shape of the model for one input: out_dims[0..2] = (h, w, c); h = w = 1 after a global pool. */
+int a3d_enc2d_output_shape(const a3d_enc2d* h, int32_t* out_dims);
+
+/* model(images, training=False)            src/module/nolbo.py:869 (backbone, head).
+ * in_dev:  [n, in_h, in_w, in_ch] NHWC on the device, in_dtype = A3D_IO_F32 (images) or the handle's operand dtype.
+ * out_dev: [n, h, w, c] NHWC ([n, c] after a global pool), out_dtype = A3D_IO_F32 or the operand dtype
+ * (a global pool always writes fp32).  Asynchronous on `stream`. */
+int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* out_dev, int out_dtype,
+                      void* stream);
+
+/* Latent split of the callers + sampling()  src/module/nolbo.py:869-875; src/module/function.py:35-38:
+ * mean = enc_out[:, :D]; logvar = clip(enc_out[:, D:2D], -clip, clip); z = mean + sqrt(exp(logvar)) * eps,
+ * eps ~ N(0,1) from Philox4x32-10 with counter (dim/4, 0x5A4D504C, obj_offset + b), key = seed (eps = 0 if
+ * seed_enable == 0).  enc_out_dev: [n, out_stride] fp32; mean/logvar/z: [n, D] fp32 (any may be NULL). */
+int a3d_enc2d_split_sample(a3d_enc2d* h, const float* enc_out_dev, int64_t n, int D, int out_stride, float clip,
+                           int seed_enable, uint64_t seed, uint64_t obj_offset, float* mean_dev, float* logvar_dev,
+                           float* z_dev, void* stream);
+
+/* Diagnostics: copy the output of layer `layer` (index into the layer list; pooled if a fused pool follows is NOT
+ * applied -- see a3d_enc2d_layer_shape) of the most recent chunk to `host` as fp32 NHWC with the padded channel
+ * count.  Synchronous. */
+int a3d_enc2d_layer_shape(const a3d_enc2d* h, int layer, int32_t* dims /* h, w, c_real, c_padded */);
+int a3d_enc2d_debug_read_layer(a3d_enc2d* h, int layer, int64_t n, float* host, size_t nbytes);
+
+int64_t a3d_enc2d_launch_count(const a3d_enc2d* h);
+size_t a3d_enc2d_workspace_bytes(const a3d_enc2d* h);
 
 const char* a3d_last_error(void);
 int a3d_abi_version(void);
