@@ -13,9 +13,9 @@
 //
 // POOL = true fuses the MaxPool2D(2, 2) that follows the convolution (darknet.py:100,104,110,116,124): the brick is
 // then at most 16 pixels wide, so the 2 x 2 partners of a pixel sit in lanes (lane ^ 1) and (lane ^ wt) of the same
-// epilogue warp: two shuffles + packed max per register pair, and each lane of the quad stores one 16-byte quarter of
-// the pooled 64-byte segment.  max() runs on the rounded 16-bit values (rounding is monotonic, so this equals
-// rounding after the pool).
+// epilogue warp: two shuffles + max per accumulator, taken BEFORE the BN shift and the activation (both monotone), so
+// the activation work drops 4x; each lane of the quad finishes and stores one 16-byte quarter of the pooled 64-byte
+// segment.
 #include <cstdlib>
 
 #include "epilogue.cuh"
@@ -26,14 +26,16 @@ namespace a3d {
 namespace {
 
 constexpr int BM = 128;
-constexpr int A_BYTES = BM * 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;   // 4 per TMEM lane quarter: the shallow layers (K = 9 steps) are epilogue-latency bound
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 
-template <int BN>
+// KC = channels per K step: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B; the 32-channel input of
+// the second Darknet19 conv, which would waste half of every MMA if padded to 64)
+template <int BN, int KC>
 struct Cfg {
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * KC * 2;
+  static constexpr int B_BYTES = BN * KC * 2;
+  static constexpr int STAGES = KC == 32 ? 12 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + NUM_BARS * 8 + 16;
 };
@@ -53,23 +55,17 @@ __device__ __forceinline__ float act2d(float v) {
   else return activate<ACT>(v);
 }
 
-__device__ __forceinline__ uint32_t max2_f16(uint32_t a, uint32_t b) {
-  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-__device__ __forceinline__ uint32_t max2_bf16(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-
 // MODE 0: 16-bit [pixels, cout_pad]; 1: fp32 [pixels, cout_real] (final head conv; feeds the global pool);
 // 2: 16-bit with the 2 x 2 max-pool fused, [n, H/2, W/2, cout_pad]
-template <int BN, int FMT, int ACT, int MODE>
+template <int BN, int KC, int FMT, int ACT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
                  void* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
                  Conv2dGeom g) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, KC>;
+  constexpr int WPQ = BN >= 128 ? 4 : 2;   // epilogue warps per lane quarter; each owns CW = BN / WPQ columns
+  constexpr int CW = BN / WPQ;
+  constexpr int A_BYTES = C::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -92,7 +88,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4 * WPQ); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -105,22 +101,30 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===================================================== TMA producer
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int nt = u % g.n_tiles, mt = u / g.n_tiles;
-        const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
-        const int w0 = tw << g.lw, h0 = th << g.lh, n0 = nb << (7 - g.lw - g.lh);
-        for (int tap = 0; tap < g.taps; ++tap) {
-          const int dy = g.taps == 9 ? tap / 3 - 1 : 0, dx = g.taps == 9 ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < g.cin_chunks; ++kc, ++it) {
-            const int s = it % C::STAGES;
-            ptx::mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+    // ===================================================== TMA producer (converged warp, elected-lane issue).  The loop
+    // body is kept to a handful of instructions -- stage / phase / tap offsets advance incrementally: with div / mod per
+    // K step this single warp needed ~700 clk per step and starved the MMA warp on the 9-step shallow layers.
+    int s = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int nt = u % g.n_tiles, mt = u / g.n_tiles;
+      const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
+      const int w0 = tw << g.lw, h0 = th << g.lh, n0 = nb << (7 - g.lw - g.lh);
+      int dy = g.taps == 9 ? -1 : 0, dx = dy;
+      int brow = nt * BN;
+      for (int tap = 0; tap < g.taps; ++tap) {
+        for (int kc = 0; kc < g.cin_chunks; ++kc) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&full[s], A_BYTES + C::B_BYTES);
-            tma_load_4d(smem_a + s * A_BYTES, &tmap_act, &full[s], kc * 64, w0 + dx, h0 + dy, n0);
-            ptx::tma_load_2d(smem_b + s * C::B_BYTES, &tmap_wgt, &full[s], kc * 64, tap * g.cout_pad + nt * BN);
+            tma_load_4d(smem_a + s * A_BYTES, &tmap_act, &full[s], kc * KC, w0 + dx, h0 + dy, n0);
+            ptx::tma_load_2d(smem_b + s * C::B_BYTES, &tmap_wgt, &full[s], kc * KC, brow);
           }
+          __syncwarp();
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
+        brow += g.cout_pad;
+        if (++dx > 1) { dx = -1; ++dy; }
       }
     }
   } else if (warp == 1) {
@@ -128,41 +132,45 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN, FMT);
     const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
     const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
-    uint32_t it = 0, unit_it = 0;
+    uint32_t unit_it = 0, ph = 0;
+    int s = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN;
-      for (int ks = 0; ks < ksteps; ++ks, ++it) {
-        const int s = it % C::STAGES;
-        ptx::mbar_wait(&full[s], (it / C::STAGES) & 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4), b_lo = b_lo0 + s * (C::B_BYTES >> 4);
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + kk * 2), ptx::sw128_desc(b_lo + kk * 2), idesc,
-                             (ks | kk) != 0);
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            if constexpr (KC == 64)
+              ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + kk * 2), ptx::sw128_desc(b_lo + kk * 2), idesc, (ks | kk) != 0);
+            else
+              ptx::umma_f16<1>(tacc, ptx::sw64_desc(a_lo + kk * 2), ptx::sw64_desc(b_lo + kk * 2), idesc, (ks | kk) != 0);
+          }
           ptx::umma_commit<1>(&empty[s]);
           if (ks == ksteps - 1) ptx::umma_commit<1>(&t_full[buf]);
         }
         __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < WPQ) {
     // ===================================================== epilogue: TMEM -> BN -> act -> global (direct 16 B stores)
     const int e = warp - 4;
     const int quarter = e & 3, chalf = e >> 2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    constexpr int GROUPS = BN / 2 / 32;   // 32-column groups per warp
+    constexpr int GROUPS = CW / 32;   // 32-column groups per warp
     uint32_t unit_it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
       const int nt = u % g.n_tiles, mt = u / g.n_tiles;
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + lane_base + buf * BN + chalf * (BN / 2);
+      const uint32_t tacc = tmem_base + lane_base + buf * BN + chalf * CW;
       const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
       const int r = quarter * 32 + lane;
       const int wi = r & ((1 << g.lw) - 1), hi = (r >> g.lw) & ((1 << g.lh) - 1), ni = r >> (g.lw + g.lh);
@@ -173,14 +181,43 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
                                   : ((int64_t)img * g.H + ph) * g.W + pw;
 #pragma unroll 1
       for (int gi = 0; gi < GROUPS; ++gi) {
-        const int co0 = nt * BN + chalf * (BN / 2) + gi * 32;
+        const int co0 = nt * BN + chalf * CW + gi * 32;
         uint32_t v[32];
         ptx::tmem_ld16(tacc + gi * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         ptx::tmem_ld16(tacc + gi * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         ptx::tmem_ld_wait();
         const float4* sc4 = reinterpret_cast<const float4*>(scale + co0);
         const float4* sh4 = reinterpret_cast<const float4*>(shift + co0);
-        if constexpr (MODE == 1) {
+        if constexpr (MODE == 2) {
+          // max-pool BEFORE shift + activation (both monotone non-decreasing): max_window act(s*a + t) ==
+          // act(max_window(s*a) + t); each lane of a 2 x 2 quad then finishes only its own 8 of the 32 channels
+          const int wt = 1 << g.lw;
+          float m[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 sc = __ldg(sc4 + i);
+            const float s4[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t = __uint_as_float(v[4 * i + j]) * s4[j];
+              t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+              t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, wt));
+              m[4 * i + j] = t;
+            }
+          }
+          const int sub = (wi & 1) | ((hi & 1) << 1);
+          const float4 sha = __ldg(sh4 + sub * 2), shb = __ldg(sh4 + sub * 2 + 1);
+          const float sh8[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = sub == 0 ? m[j] : sub == 1 ? m[8 + j] : sub == 2 ? m[16 + j] : m[24 + j];
+            y[j] = act2d<ACT>(t + sh8[j]);
+          }
+          if (row_ok)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0 + sub * 8) =
+                make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+        } else if constexpr (MODE == 1) {
           float* dst = reinterpret_cast<float*>(out) + p * g.cout_real + co0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -208,24 +245,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
           }
-          if constexpr (MODE == 2) {
-            const int wt = 1 << g.lw;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              uint32_t t = __shfl_xor_sync(0xffffffffu, o[i], 1);
-              o[i] = FMT == A3D_DTYPE_F16 ? max2_f16(o[i], t) : max2_bf16(o[i], t);
-              t = __shfl_xor_sync(0xffffffffu, o[i], wt);
-              o[i] = FMT == A3D_DTYPE_F16 ? max2_f16(o[i], t) : max2_bf16(o[i], t);
-            }
-            const int sub = (wi & 1) | ((hi & 1) << 1);
-            uint4 q;
-            q.x = sub == 0 ? o[0] : sub == 1 ? o[4] : sub == 2 ? o[8] : o[12];
-            q.y = sub == 0 ? o[1] : sub == 1 ? o[5] : sub == 2 ? o[9] : o[13];
-            q.z = sub == 0 ? o[2] : sub == 1 ? o[6] : sub == 2 ? o[10] : o[14];
-            q.w = sub == 0 ? o[3] : sub == 1 ? o[7] : sub == 2 ? o[11] : o[15];
-            if (row_ok)
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0 + sub * 8) = q;
-          } else if (row_ok) {
+          if (row_ok) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
@@ -243,36 +263,36 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int BN, int FMT, int MODE>
+template <int BN, int KC, int FMT, int MODE>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const float* scale, const float* shift,
               const Conv2dGeom& g, int act, int grid, cudaStream_t st) {
   auto launch = [&](auto kern) -> int {
-    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-    kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
+    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KC>::SMEM_BYTES));
+    kern<<<grid, kThreads, Cfg<BN, KC>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };
   switch (act) {
-    case A3D_ACT_ELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_ELU, MODE>);
-    case A3D_ACT_RELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_RELU, MODE>);
-    case A3D_ACT_LRELU: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_LRELU, MODE>);
-    case A3D_ACT_LRELU01: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_LRELU01, MODE>);
-    case A3D_ACT_NONE: return launch(conv2d_tc_kernel<BN, FMT, A3D_ACT_NONE, MODE>);
+    case A3D_ACT_ELU: return launch(conv2d_tc_kernel<BN, KC, FMT, A3D_ACT_ELU, MODE>);
+    case A3D_ACT_RELU: return launch(conv2d_tc_kernel<BN, KC, FMT, A3D_ACT_RELU, MODE>);
+    case A3D_ACT_LRELU: return launch(conv2d_tc_kernel<BN, KC, FMT, A3D_ACT_LRELU, MODE>);
+    case A3D_ACT_LRELU01: return launch(conv2d_tc_kernel<BN, KC, FMT, A3D_ACT_LRELU01, MODE>);
+    case A3D_ACT_NONE: return launch(conv2d_tc_kernel<BN, KC, FMT, A3D_ACT_NONE, MODE>);
     default: set_error("conv2d: unsupported activation %d", act); return A3D_ERR_INVALID;
   }
 }
 
-template <int BN>
+template <int BN, int KC>
 int launch_fmt(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const float* scale, const float* shift,
                const Conv2dGeom& g, int fmt, int act, int mode, int grid, cudaStream_t st) {
   if (fmt == A3D_DTYPE_F16) {
-    if (mode == 0) return launch_bn<BN, A3D_DTYPE_F16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
-    if (mode == 1) return launch_bn<BN, A3D_DTYPE_F16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
-    return launch_bn<BN, A3D_DTYPE_F16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
+    if (mode == 0) return launch_bn<BN, KC, A3D_DTYPE_F16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
+    if (mode == 1) return launch_bn<BN, KC, A3D_DTYPE_F16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
+    return launch_bn<BN, KC, A3D_DTYPE_F16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
   }
-  if (mode == 0) return launch_bn<BN, A3D_DTYPE_BF16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
-  if (mode == 1) return launch_bn<BN, A3D_DTYPE_BF16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
-  return launch_bn<BN, A3D_DTYPE_BF16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
+  if (mode == 0) return launch_bn<BN, KC, A3D_DTYPE_BF16, 0>(ta, tw, out, scale, shift, g, act, grid, st);
+  if (mode == 1) return launch_bn<BN, KC, A3D_DTYPE_BF16, 1>(ta, tw, out, scale, shift, g, act, grid, st);
+  return launch_bn<BN, KC, A3D_DTYPE_BF16, 2>(ta, tw, out, scale, shift, g, act, grid, st);
 }
 
 }  // namespace
@@ -291,9 +311,12 @@ int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, v
   const int grid = total < num_sms ? total : num_sms;
   const int mode = out_f32 ? 1 : (pool ? 2 : 0);
   int rc;
-  if (bn == 256) rc = launch_fmt<256>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
-  else if (bn == 128) rc = launch_fmt<128>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
-  else rc = launch_fmt<64>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  if (g.kc == 32) {
+    if (bn != 64) { set_error("conv2d: 32-channel K steps are built for 64-wide N tiles only"); return A3D_ERR_INVALID; }
+    rc = launch_fmt<64, 32>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  } else if (bn == 256) rc = launch_fmt<256, 64>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  else if (bn == 128) rc = launch_fmt<128, 64>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
+  else rc = launch_fmt<64, 64>(tmap_act, tmap_wgt, out, scale, shift, g, fmt, act, mode, grid, st);
   if (rc == A3D_OK && launches) ++*launches;
   return rc;
 }

@@ -6,9 +6,12 @@
 // Execution plan: a conv followed by a max-pool becomes ONE launch (pool fused into the epilogue); the 3-channel first
 // layer runs on CUDA cores (K = 27); every other conv is a tcgen05 implicit GEMM; a final conv followed by a global
 // pool writes fp32 and a small reduction kernel produces [n, C].  All hidden activations are 16-bit NHWC with the
-// channel count padded to a multiple of 64 (pad channels are zero: zero weights rows/scale 0/shift 0).
+// channel count padded to a multiple of 64 (pad channels are zero: zero weight rows / scale 0 / shift 0); the 32-channel
+// output of the image layer stays 32 wide and the conv that reads it runs 32-channel K steps (SWIZZLE_64B operands).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "internal.h"
 
@@ -29,7 +32,8 @@ struct Op2d {
   int bn_tile = 0;
   Conv2dGeom g;
   CUtensorMap tmap_act, tmap_wgt;
-  void* wgt = nullptr;        // device: 16-bit [tap][cout_pad][cin_pad], or fp32 [27][32] (first layer)
+  void* wgt = nullptr;        // device: 16-bit [tap][cout_pad][cin_pad]; first layer: fp32 [27][32] (CUDA-core kernel)
+  void* wgt_first16 = nullptr; // first layer, tensor-core kernel: 16-bit [32 co][32 k], k = tap*3 + ci, 5 zero columns
   float *scale = nullptr, *shift = nullptr;
 };
 
@@ -63,6 +67,7 @@ struct a3d_enc2d {
   int64_t launches = 0;
   int64_t last_n = 0;
   int sticky = 0;
+  bool first_simt = false;    // A3D_ENC_FIRST=simt: CUDA-core image layer (diagnostic cross-check of the tensor-core one)
 };
 
 namespace {
@@ -88,7 +93,8 @@ void choose_brick(Op2d& op) {
   g.lw = ilog2(wt); g.lh = ilog2(ht);
   g.tiles_w = W / wt; g.tiles_h = H / ht;
   g.taps = op.ksize * op.ksize;
-  g.cin_chunks = op.cin_pad / 64;
+  g.kc = op.cin_pad % 64 == 0 ? 64 : 32;
+  g.cin_chunks = op.cin_pad / g.kc;
   g.cout_pad = op.cout_pad;
   g.cout_real = op.cout;
   g.n_tiles = op.cout_pad / op.bn_tile;
@@ -121,7 +127,7 @@ int build_plan(a3d_enc2d* h) {
       }
       Op2d op;
       op.layer = li; op.H = H; op.W = W; op.cin = C; op.cin_pad = C_pad; op.cout = L.filters;
-      op.cout_pad = round_up(L.filters, 64); op.ksize = L.ksize; op.act = L.activation; op.bn = L.batch_norm != 0;
+      op.cout_pad = cur < 0 ? 32 : round_up(L.filters, 64); op.ksize = L.ksize; op.act = L.activation; op.bn = L.batch_norm != 0;
       op.in_buf = cur; op.w_index = w_index;
       h->w_numel.push_back((int64_t)L.ksize * L.ksize * C * L.filters);
       if (op.bn) for (int i = 0; i < 4; ++i) h->w_numel.push_back(L.filters);
@@ -138,7 +144,7 @@ int build_plan(a3d_enc2d* h) {
         op.pool = next_pool;
         op.out_f32 = next_gpool;
         if (op.pool && ((H & 1) || (W & 1))) { set_error("layer %d: max-pool on an odd size", li); return A3D_ERR_INVALID; }
-        op.bn_tile = conv2d_tc_bn(op.cout_pad);
+        op.bn_tile = op.cin_pad % 64 == 0 ? conv2d_tc_bn(op.cout_pad) : 64;   // 32-channel K steps: N tile 64 only
         choose_brick(op);
         if (op.pool && op.g.lh < 1) { set_error("layer %d: fused pool needs H >= 2", li); return A3D_ERR_INVALID; }
       }
@@ -218,15 +224,17 @@ int make_maps(a3d_enc2d* h, Op2d& op) {
   const uint64_t C = op.cin_pad, W = op.W, H = op.H;
   cuuint64_t dims[4] = {C, W, H, (cuuint64_t)b.alloc_n};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, 1u << op.g.lw, 1u << op.g.lh, 128u >> (op.g.lw + op.g.lh)};
+  const cuuint32_t kc = (cuuint32_t)op.g.kc;
+  const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  cuuint32_t box[4] = {kc, 1u << op.g.lw, 1u << op.g.lh, 128u >> (op.g.lw + op.g.lh)};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(&op.tmap_act, dt, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder activations, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
   cuuint64_t wd[2] = {C, (cuuint64_t)op.ksize * op.ksize * op.cout_pad};
   cuuint64_t ws[1] = {C * 2};
-  cuuint32_t wb[2] = {64, (cuuint32_t)op.bn_tile};
-  r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  cuuint32_t wb[2] = {kc, (cuuint32_t)op.bn_tile};
+  r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder weights, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
   return A3D_OK;
@@ -252,6 +260,10 @@ int finalize(a3d_enc2d* h) {
     const int taps = op.ksize * op.ksize;
     if (op.kind == OP_FIRST) {
       if ((rc = upload(k.data(), k.size() * 4, &op.wgt))) return rc;   // already [tap][ci][co] = [27][32]
+      p16.assign(32 * 32, cvt16(0.f, fmt));
+      for (int kk = 0; kk < 27; ++kk)
+        for (int co = 0; co < 32; ++co) p16[(size_t)co * 32 + kk] = cvt16(k[(size_t)kk * 32 + co], fmt);
+      if ((rc = upload(p16.data(), p16.size() * 2, &op.wgt_first16))) return rc;
     } else {
       p16.assign((size_t)taps * op.cout_pad * op.cin_pad, cvt16(0.f, fmt));
       for (int t = 0; t < taps; ++t)
@@ -280,6 +292,10 @@ int run_chunk(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* o
     void* out = op.out_buf >= 0 ? h->bufs[op.out_buf].ptr : out_dev;
     switch (op.kind) {
       case OP_FIRST:
+        if (!h->first_simt)
+          rc = launch_conv2d_first_tc(reinterpret_cast<const float*>(in_dev), op.wgt_first16, op.scale, op.shift, out, n,
+                                      op.H, op.W, op.cout_pad, fmt, op.act, h->num_sms, st, &h->launches);
+        else
         rc = launch_conv2d_first_pool(reinterpret_cast<const float*>(in_dev), reinterpret_cast<const float*>(op.wgt),
                                       op.scale, op.shift, out, n, op.H, op.W, op.cout_pad, fmt, op.act, st, &h->launches);
         break;
@@ -346,6 +362,7 @@ int a3d_enc2d_create(const a3d_enc2d_desc* d, a3d_enc2d** out) {
   }
   cudaSetDevice(d->device);
   h->num_sms = prop.multiProcessorCount;
+  { const char* e = getenv("A3D_ENC_FIRST"); h->first_simt = e && std::string(e) == "simt"; }
   if ((rc = alloc_arena(h))) { a3d_enc2d_destroy(h); return rc; }
   *out = h;
   return A3D_OK;
@@ -355,7 +372,7 @@ void a3d_enc2d_destroy(a3d_enc2d* h) {
   if (!h) return;
   cudaDeviceSynchronize();
   for (auto& b : h->bufs) cudaFree(b.ptr);
-  for (auto& op : h->ops) { cudaFree(op.wgt); cudaFree(op.scale); cudaFree(op.shift); }
+  for (auto& op : h->ops) { cudaFree(op.wgt); cudaFree(op.wgt_first16); cudaFree(op.scale); cudaFree(op.shift); }
   delete h;
 }
 

@@ -92,6 +92,7 @@ struct Conv2dGeom {
   int tiles_w = 0, tiles_h = 0;
   int m_tiles = 0, n_tiles = 0;
   int taps = 0, cin_chunks = 0, cout_pad = 0, cout_real = 0;
+  int kc = 64;                 // channels per K step (64: SWIZZLE_128B rows, 32: SWIZZLE_64B rows)
   int n_images = 0;
 };
 int conv2d_tc_bn(int cout_pad);
@@ -102,6 +103,10 @@ int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, v
 // first layer: Conv2D(3 -> 32, k3) + BN + act + MaxPool2D(2,2); in fp32 [n,H,W,3], out 16-bit [n,H/2,W/2,cout_pad]
 int launch_conv2d_first_pool(const float* in, const float* w27x32, const float* scale, const float* shift, void* out,
                              int64_t n, int H, int W, int cout_pad, int fmt, int act, cudaStream_t st, int64_t* launches);
+// same layer on the tensor cores (conv2d_first_tc.cu): w32x32 = 16-bit [co][k = tap*3+ci], zero-padded to K = 32
+int launch_conv2d_first_tc(const float* in, const void* w32x32, const float* scale, const float* shift, void* out,
+                           int64_t n, int H, int W, int cout_pad, int fmt, int act, int num_sms, cudaStream_t st,
+                           int64_t* launches);
 int launch_maxpool2d(const void* in, void* out, int64_t n, int H, int W, int C, int fmt, cudaStream_t st,
                      int64_t* launches);
 int launch_global_pool(const float* in, float* out, int64_t n, int HW, int C, int is_max, cudaStream_t st,

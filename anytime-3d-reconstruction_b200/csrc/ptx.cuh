@@ -197,6 +197,10 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, u
 constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t lo) { return ((uint64_t)kSw128DescHi << 32) | lo; }
+// 64-byte-swizzled K-major operand (rows of 64 bytes = 32 x 16-bit, 8-row atoms of 512 bytes, Swizzle<2,4,3>):
+// layout type 4, SBO = 512 B.  Advancing K by 16 elements = +32 bytes of start address, as for SWIZZLE_128B.
+constexpr uint32_t kSw64DescHi = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t sw64_desc(uint32_t lo) { return ((uint64_t)kSw64DescHi << 32) | lo; }
 // Instruction descriptor for kind::f16: fp32 accumulate, both operands K-major, format 0 = f16 / 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
