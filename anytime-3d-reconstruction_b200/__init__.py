@@ -169,11 +169,34 @@ class Decoder3D:
             out.append(a)
         return out
 
-    def save_weights(self, path: str) -> None:
-        """Keras-order arrays in an .npz (TF-checkpoint bundles need TensorFlow)."""
+    def _layer_var_names(self) -> list[list[str]]:
+        """Variable names per weighted Keras layer in get_weights() order (autoencoder3D.py:122-132)."""
+        bn = ['gamma', 'beta', 'moving_mean', 'moving_variance']
+        names = [['kernel', 'bias'], bn]
+        n = len(self._s['filters'])
+        for i in range(n):
+            names.append(['kernel'])
+            if i < n - 1:
+                names.append(bn)
+        return names
+
+    def save_weights(self, path: str, save_format: str | None = None) -> None:
+        """nolbo.py:1572-1574.  ``save_format='tf'`` (Keras' default for a prefix without extension) writes a TensorFlow
+        tensor-bundle checkpoint (``path.index`` + ``path.data-00000-of-00001``, tf_checkpoint.py); otherwise the
+        Keras-order arrays go into an .npz."""
+        if save_format == 'tf':
+            from . import tf_checkpoint
+            tf_checkpoint.save_keras_weights(path, self.get_weights(), self._layer_var_names())
+            return
         np.savez(path if path.endswith('.npz') else path + '.npz', *self.get_weights())
 
     def load_weights(self, path: str) -> None:
+        """nolbo.py:1585-1592: accepts the checkpoint prefix Keras ``save_weights`` wrote (TF tensor bundle, read without
+        TensorFlow by tf_checkpoint.py) or an .npz of Keras-order arrays."""
+        from . import tf_checkpoint
+        if tf_checkpoint.is_checkpoint(path):
+            self.set_weights(tf_checkpoint.load_keras_weights(path))
+            return
         p = path if os.path.exists(path) else path + '.npz'
         with np.load(p) as f:
             self.set_weights([f[f'arr_{i}'] for i in range(len(f.files))])

@@ -87,6 +87,7 @@ SIGNATURES = {
     'a3d_enc2d_debug_read_layer': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]),
     'a3d_enc2d_launch_count': (C.c_int64, [C.c_void_p]),
     'a3d_enc2d_workspace_bytes': (C.c_size_t, [C.c_void_p]),
+    'a3d_crc32c': (C.c_uint32, [C.c_void_p, C.c_size_t, C.c_uint32]),
     'a3d_last_error': (C.c_char_p, []),
     'a3d_abi_version': (C.c_int, []),
 }

@@ -427,6 +427,35 @@ void collect_profile(a3d_handle* h, cudaStream_t st, bool first) {
 extern "C" {
 
 int a3d_abi_version(void) { return A3D_ABI_VERSION; }
+
+uint32_t a3d_crc32c(const void* data, size_t n, uint32_t crc) {
+  static uint32_t tbl[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tbl[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tbl[t][i] = (tbl[t - 1][i] >> 8) ^ tbl[0][tbl[t - 1][i] & 0xFF];
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n >= 8) {   // slice-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tbl[7][lo & 0xFF] ^ tbl[6][(lo >> 8) & 0xFF] ^ tbl[5][(lo >> 16) & 0xFF] ^ tbl[4][lo >> 24] ^
+        tbl[3][hi & 0xFF] ^ tbl[2][(hi >> 8) & 0xFF] ^ tbl[1][(hi >> 16) & 0xFF] ^ tbl[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tbl[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
 const char* a3d_last_error(void) { return g_err; }
 
 int a3d_create(const a3d_desc* d, a3d_handle** out) {

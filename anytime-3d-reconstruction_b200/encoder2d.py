@@ -149,10 +149,28 @@ class Encoder2D:
             out.append(a)
         return out
 
-    def save_weights(self, path: str) -> None:
+    def _layer_var_names(self) -> list[list[str]]:
+        names = []
+        for l in self.layers:
+            if l['kind'] == 'conv':
+                names.append(['kernel'])
+                if l['bn']:
+                    names.append(['gamma', 'beta', 'moving_mean', 'moving_variance'])
+        return names
+
+    def save_weights(self, path: str, save_format: str | None = None) -> None:
+        """``save_format='tf'``: TensorFlow tensor-bundle checkpoint like Keras writes; default: .npz."""
+        if save_format == 'tf':
+            from . import tf_checkpoint
+            tf_checkpoint.save_keras_weights(path, self.get_weights(), self._layer_var_names())
+            return
         np.savez(path if path.endswith('.npz') else path + '.npz', *self.get_weights())
 
     def load_weights(self, path: str) -> None:
+        from . import tf_checkpoint
+        if tf_checkpoint.is_checkpoint(path):
+            self.set_weights(tf_checkpoint.load_keras_weights(path))
+            return
         p = path if os.path.exists(path) else path + '.npz'
         with np.load(p) as f:
             self.set_weights([f[f'arr_{i}'] for i in range(len(f.files))])

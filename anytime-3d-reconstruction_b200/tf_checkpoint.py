@@ -1,0 +1,372 @@
+"""Reader / writer for the TensorFlow "tensor bundle" checkpoints that Keras ``model.save_weights(prefix)`` produces
+(``prefix.index`` + ``prefix.data-00000-of-00001``), so weights trained with the reference drop into
+``Decoder3D.load_weights`` / ``Encoder2D.load_weights`` (reference call sites
+src/module/nolbo.py:1568-1592: ``self._decoder.save_weights(os.path.join(save_path, name))`` / ``load_weights``).
+
+Pure host code, no TensorFlow needed.  The format is third-party (TensorFlow ``tensor_bundle`` on top of the LevelDB
+table format) and is restated here from its published layout -- PARITY UNPINNED: no TensorFlow is installable in this
+environment, so the reader is tested against the writer below and against hand-built byte strings, not against a file
+written by TensorFlow itself.
+
+Layout:
+* ``.index``: LevelDB SSTable.  Blocks of prefix-compressed (key, value) entries followed by a restart array; each block
+  is followed by a 5-byte trailer (compression type: 0 raw / 1 snappy, masked CRC32C).  48-byte footer: metaindex
+  handle, index handle (varint64 offset + size), zero padding to 40 bytes, magic 0xdb4775248b80fb57.
+  Key ``""`` -> BundleHeaderProto; every other key is a tensor name -> BundleEntryProto
+  {1: dtype, 2: TensorShapeProto, 3: shard_id, 4: offset, 5: size, 6: crc32c (fixed32)}.
+* ``.data-NNNNN-of-MMMMM``: raw little-endian tensor bytes at ``offset``.
+* Keras object-graph keys: ``layer_with_weights-<i>/<var>/.ATTRIBUTES/VARIABLE_VALUE`` with ``<var>`` in
+  {kernel, bias, gamma, beta, moving_mean, moving_variance}; ``i`` counts the layers that own variables in
+  ``model.layers`` order, which is also the ``get_weights()`` order.
+"""
+from __future__ import annotations
+
+import os
+import re
+import struct
+
+import numpy as np
+
+_MAGIC = 0xdb4775248b80fb57
+_DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: np.int8, 9: np.int64, 10: np.bool_,
+           19: np.float16}
+_DT_BFLOAT16 = 14
+_DTYPE_CODES = {np.dtype(v): k for k, v in _DTYPES.items()}
+_VAR_ORDER = ['kernel', 'bias', 'gamma', 'beta', 'moving_mean', 'moving_variance']
+
+
+# ------------------------------------------------------------------------------------------------ primitives
+def _varint(buf: bytes, pos: int) -> tuple[int, int]:
+    out = shift = 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        out |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return out, pos
+        shift += 7
+
+
+def _put_varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _crc32c_table():
+    tbl = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tbl.append(c)
+    return tbl
+
+
+_CRC_TABLE = _crc32c_table()
+
+
+def crc32c(data: bytes, crc: int = 0) -> int:
+    """CRC-32C (Castagnoli).  Large buffers go through liba3d's slice-by-8 host routine (a3d_crc32c); the pure-Python
+    loop below is the same polynomial and serves small index blocks or a missing library (this is file I/O, not the
+    compute path)."""
+    if len(data) >= 4096:
+        try:
+            from . import _capi
+            buf = bytes(data)
+            return int(_capi.lib().a3d_crc32c(buf, len(buf), crc))
+        except (RuntimeError, OSError, AttributeError):
+            pass
+    c = crc ^ 0xFFFFFFFF
+    for b in data:
+        c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def _mask_crc(c: int) -> int:
+    return (((c >> 15) | (c << 17)) + 0xa282ead8) & 0xFFFFFFFF
+
+
+def _snappy_decompress(buf: bytes) -> bytes:
+    n, pos = _varint(buf, 0)
+    out = bytearray()
+    while pos < len(buf):
+        tag = buf[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:                                  # literal
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(buf[pos:pos + nb], 'little')
+                pos += nb
+            ln += 1
+            out += buf[pos:pos + ln]
+            pos += ln
+            continue
+        if kind == 1:
+            ln = ((tag >> 2) & 7) + 4
+            off = ((tag >> 5) << 8) | buf[pos]
+            pos += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[pos:pos + 2], 'little')
+            pos += 2
+        else:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[pos:pos + 4], 'little')
+            pos += 4
+        if off == 0 or off > len(out):
+            raise ValueError('corrupt snappy block')
+        for _ in range(ln):                            # overlapping copies are legal
+            out.append(out[-off])
+    if len(out) != n:
+        raise ValueError('snappy length mismatch')
+    return bytes(out)
+
+
+def _proto_fields(buf: bytes):
+    """Yield (field number, wire type, value) of a serialized protobuf message (varint / fixed / length-delimited)."""
+    pos = 0
+    while pos < len(buf):
+        key, pos = _varint(buf, pos)
+        fn, wt = key >> 3, key & 7
+        if wt == 0:
+            v, pos = _varint(buf, pos)
+        elif wt == 1:
+            v = buf[pos:pos + 8]
+            pos += 8
+        elif wt == 2:
+            ln, pos = _varint(buf, pos)
+            v = buf[pos:pos + ln]
+            pos += ln
+        elif wt == 5:
+            v = buf[pos:pos + 4]
+            pos += 4
+        else:
+            raise ValueError(f'unsupported protobuf wire type {wt}')
+        yield fn, wt, v
+
+
+# ------------------------------------------------------------------------------------------------ table reader
+def _read_block(data: bytes, offset: int, size: int, verify: bool) -> bytes:
+    raw = data[offset:offset + size]
+    ctype = data[offset + size]
+    if verify:
+        want = struct.unpack('<I', data[offset + size + 1:offset + size + 5])[0]
+        if _mask_crc(crc32c(data[offset:offset + size + 1])) != want:
+            raise ValueError('checkpoint index: block checksum mismatch')
+    if ctype == 0:
+        return raw
+    if ctype == 1:
+        return _snappy_decompress(raw)
+    raise ValueError(f'checkpoint index: unknown block compression {ctype}')
+
+
+def _block_entries(block: bytes):
+    n_restarts = struct.unpack('<I', block[-4:])[0]
+    end = len(block) - 4 - 4 * n_restarts
+    pos, key = 0, b''
+    while pos < end:
+        shared, pos = _varint(block, pos)
+        non_shared, pos = _varint(block, pos)
+        vlen, pos = _varint(block, pos)
+        key = key[:shared] + block[pos:pos + non_shared]
+        pos += non_shared
+        yield key, block[pos:pos + vlen]
+        pos += vlen
+
+
+def read_index(path: str, verify: bool = True) -> dict[bytes, bytes]:
+    """All (key, value) pairs of an SSTable file."""
+    data = open(path, 'rb').read()
+    if len(data) < 48 or struct.unpack('<Q', data[-8:])[0] != _MAGIC:
+        raise ValueError(f'{path} is not a TensorFlow checkpoint index (bad magic)')
+    footer = data[-48:]
+    _, pos = _varint(footer, 0)          # metaindex handle (offset, size): unused
+    _, pos = _varint(footer, pos)
+    ioff, pos = _varint(footer, pos)
+    isize, pos = _varint(footer, pos)
+    out = {}
+    for _, handle in _block_entries(_read_block(data, ioff, isize, verify)):
+        boff, p = _varint(handle, 0)
+        bsize, p = _varint(handle, p)
+        for k, v in _block_entries(_read_block(data, boff, bsize, verify)):
+            out[k] = v
+    return out
+
+
+def _parse_entry(buf: bytes) -> dict:
+    e = {'dtype': 0, 'shape': [], 'shard_id': 0, 'offset': 0, 'size': 0, 'crc32c': None, 'slices': False}
+    for fn, wt, v in _proto_fields(buf):
+        if fn == 1:
+            e['dtype'] = v
+        elif fn == 2:
+            for f2, _, v2 in _proto_fields(v):
+                if f2 == 2:
+                    size = 0
+                    for f3, _, v3 in _proto_fields(v2):
+                        if f3 == 1:
+                            size = v3
+                    e['shape'].append(size)
+        elif fn == 3:
+            e['shard_id'] = v
+        elif fn == 4:
+            e['offset'] = v
+        elif fn == 5:
+            e['size'] = v
+        elif fn == 6:
+            e['crc32c'] = struct.unpack('<I', v)[0]
+        elif fn == 7:
+            e['slices'] = True
+    return e
+
+
+def load_checkpoint(prefix: str, verify: bool = True) -> dict[str, np.ndarray]:
+    """name -> array for every numeric tensor of the checkpoint ``prefix`` (string tensors such as
+    ``_CHECKPOINTABLE_OBJECT_GRAPH`` are skipped)."""
+    index = read_index(prefix + '.index', verify)
+    num_shards = 1
+    for fn, _, v in _proto_fields(index.get(b'', b'')):
+        if fn == 1:
+            num_shards = v
+        elif fn == 2 and v != 0:
+            raise ValueError('big-endian checkpoints are not supported')
+    shards: dict[int, bytes] = {}
+    out = {}
+    for key, val in index.items():
+        if key == b'':
+            continue
+        e = _parse_entry(val)
+        if e['slices']:
+            raise ValueError(f'{key!r}: partitioned (sliced) variables are not supported')
+        if e['dtype'] == _DT_BFLOAT16:
+            np_dt = None
+        elif e['dtype'] in _DTYPES:
+            np_dt = np.dtype(_DTYPES[e['dtype']])
+        else:
+            continue                                   # DT_STRING etc.
+        sid = e['shard_id']
+        if sid not in shards:
+            shards[sid] = open(f'{prefix}.data-{sid:05d}-of-{num_shards:05d}', 'rb').read()
+        raw = shards[sid][e['offset']:e['offset'] + e['size']]
+        if len(raw) != e['size']:
+            raise ValueError(f'{key!r}: data file is truncated')
+        if verify and e['crc32c'] is not None and _mask_crc(crc32c(raw)) != e['crc32c']:
+            raise ValueError(f'{key!r}: tensor checksum mismatch')
+        if np_dt is None:
+            a = (np.frombuffer(raw, '<u2').astype(np.uint32) << 16).view(np.float32)
+        else:
+            a = np.frombuffer(raw, np_dt.newbyteorder('<'))
+        out[key.decode('utf-8')] = a.reshape(e['shape']).copy()
+    return out
+
+
+_KERAS_KEY = re.compile(r'^layer_with_weights-(\d+)/([A-Za-z_]+)/\.ATTRIBUTES/VARIABLE_VALUE$')
+
+
+def keras_weight_list(tensors: dict[str, np.ndarray]) -> list[np.ndarray]:
+    """Order the variables of a Keras object-graph checkpoint like ``model.get_weights()``: by layer index, then
+    kernel, bias, gamma, beta, moving_mean, moving_variance (trainable before non-trainable within a layer)."""
+    found = []
+    for name, a in tensors.items():
+        m = _KERAS_KEY.match(name)
+        if m and m.group(2) in _VAR_ORDER:
+            found.append((int(m.group(1)), _VAR_ORDER.index(m.group(2)), a))
+    if not found:
+        raise ValueError('no layer_with_weights-*/<var>/.ATTRIBUTES/VARIABLE_VALUE keys: not a Keras save_weights checkpoint')
+    found.sort(key=lambda t: (t[0], t[1]))
+    return [np.asarray(a, np.float32) for _, _, a in found]
+
+
+def load_keras_weights(prefix: str, verify: bool = True) -> list[np.ndarray]:
+    return keras_weight_list(load_checkpoint(prefix, verify))
+
+
+def is_checkpoint(prefix: str) -> bool:
+    return os.path.exists(prefix + '.index')
+
+
+# ------------------------------------------------------------------------------------------------ writer
+def _proto_varint(fn: int, v: int) -> bytes:
+    return _put_varint(fn << 3) + _put_varint(v)
+
+
+def _proto_bytes(fn: int, b: bytes) -> bytes:
+    return _put_varint((fn << 3) | 2) + _put_varint(len(b)) + b
+
+
+def _build_block(entries: list[tuple[bytes, bytes]], restart_interval: int = 16) -> bytes:
+    out = bytearray()
+    restarts = []
+    prev = b''
+    for i, (k, v) in enumerate(entries):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                shared += 1
+        out += _put_varint(shared) + _put_varint(len(k) - shared) + _put_varint(len(v)) + k[shared:] + v
+        prev = k
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        out += struct.pack('<I', r)
+    out += struct.pack('<I', len(restarts))
+    return bytes(out)
+
+
+def save_checkpoint(prefix: str, tensors: dict[str, np.ndarray], block_entries: int = 64) -> None:
+    """Write ``tensors`` as a single-shard tensor bundle (uncompressed blocks) readable by ``load_checkpoint`` and laid
+    out like TensorFlow's BundleWriter output."""
+    data = bytearray()
+    items = [(b'', _proto_varint(1, 1) + _proto_bytes(3, _proto_varint(1, 1)))]   # num_shards = 1, version.producer = 1
+    for name in sorted(tensors):
+        a = np.asarray(tensors[name])
+        code = _DTYPE_CODES.get(a.dtype)
+        if code is None:
+            raise ValueError(f'{name}: unsupported dtype {a.dtype}')
+        raw = a.astype(a.dtype.newbyteorder('<')).tobytes(order='C')
+        shape = b''.join(_proto_bytes(2, _proto_varint(1, int(d))) for d in a.shape)
+        entry = (_proto_varint(1, code) + _proto_bytes(2, shape) + (_proto_varint(4, len(data)) if len(data) else b'') +
+                 _proto_varint(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack('<I', _mask_crc(crc32c(raw))))
+        items.append((name.encode('utf-8'), entry))
+        data += raw
+    items.sort(key=lambda kv: kv[0])
+    table = bytearray()
+
+    def emit(block: bytes) -> bytes:
+        off = len(table)
+        table.extend(block)
+        trailer = b'\x00'
+        table.extend(trailer + struct.pack('<I', _mask_crc(crc32c(block + trailer))))
+        return _put_varint(off) + _put_varint(len(block))
+
+    index_entries = []
+    for i in range(0, len(items), block_entries):
+        chunk = items[i:i + block_entries]
+        index_entries.append((chunk[-1][0], emit(_build_block(chunk))))
+    meta = emit(_build_block([]))
+    idx = emit(_build_block(index_entries, restart_interval=1))
+    footer = meta + idx
+    footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', _MAGIC)
+    table.extend(footer)
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    with open(prefix + '.index', 'wb') as f:
+        f.write(bytes(table))
+    with open(prefix + '.data-00000-of-00001', 'wb') as f:
+        f.write(bytes(data))
+
+
+def save_keras_weights(prefix: str, weights: list[np.ndarray], layer_var_names: list[list[str]]) -> None:
+    """Write a Keras-style object-graph checkpoint: ``layer_var_names[i]`` lists the variable names of weighted layer
+    ``i`` in get_weights() order (e.g. [['kernel', 'bias'], ['gamma', 'beta', 'moving_mean', 'moving_variance'], ...])."""
+    tensors, it = {}, iter(weights)
+    for i, names in enumerate(layer_var_names):
+        for n in names:
+            tensors[f'layer_with_weights-{i}/{n}/.ATTRIBUTES/VARIABLE_VALUE'] = np.asarray(next(it), np.float32)
+    save_checkpoint(prefix, tensors)

@@ -214,6 +214,11 @@ int a3d_enc2d_debug_read_layer(a3d_enc2d* h, int layer, int64_t n, float* host, 
 int64_t a3d_enc2d_launch_count(const a3d_enc2d* h);
 size_t a3d_enc2d_workspace_bytes(const a3d_enc2d* h);
 
+/* Host utility for the TensorFlow-checkpoint reader (anytime-3d-reconstruction_b200/tf_checkpoint.py; reference weights
+ * are Keras save_weights bundles, src/module/nolbo.py:1568-1592): CRC-32C (Castagnoli) of `n` bytes, continuing from
+ * `crc` (0 to start).  Pure host code, no device needed. */
+uint32_t a3d_crc32c(const void* data, size_t n, uint32_t crc);
+
 const char* a3d_last_error(void);
 int a3d_abi_version(void);
 

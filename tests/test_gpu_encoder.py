@@ -205,3 +205,32 @@ def test_errors_like_the_reference_boundary(a3d_mod):
     enc.close()
     with pytest.raises(RuntimeError, match='global pool'):
         a3d_mod.Encoder2D([{'kind': 'global_max'}], (8, 8, 64))
+
+
+def test_tf_checkpoint_weight_io_round_trip(a3d_mod, tmp_path):
+    """nolbo.py:1568-1592: save_weights(prefix) / load_weights(prefix) through the TensorFlow tensor-bundle format
+    (read and written without TensorFlow, a3d.tf_checkpoint) for the decoder and the encoder models."""
+    dws = dr.trained_like_weights(dr.PASCAL_DECODER, 103)
+    dec = a3d_mod.decoder3D(a3d_mod.presets.PASCAL_DECODER, max_chunk=32)
+    dec.set_weights(dws)
+    z = dr.round_bf16(np.random.default_rng(2).standard_normal((2, 16)).astype(np.float32))
+    want = dec(z)
+    prefix = str(tmp_path / 'weights' / 'decoder')
+    dec.save_weights(prefix, save_format='tf')
+    assert os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
+    dec2 = a3d_mod.decoder3D(a3d_mod.presets.PASCAL_DECODER, max_chunk=32)
+    dec2.load_weights(prefix)
+    assert all(np.array_equal(a, b) for a, b in zip(dec2.get_weights(), dws))
+    assert np.array_equal(dec2(z), want)
+    dec.close(); dec2.close()
+    layers = er.layer_list()
+    ews = er.keras_default_weights(layers, 3, seed=9)
+    enc = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(32, 32), max_batch=2)
+    enc.set_weights(ews)
+    eprefix = str(tmp_path / 'weights' / 'nolbo_backbone')
+    enc.save_weights(eprefix, save_format='tf')
+    enc2 = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(32, 32), max_batch=2)
+    enc2.load_weights(eprefix)
+    x = _images(32, 2, 6)
+    assert np.array_equal(enc(x), enc2(x))
+    enc.close(); enc2.close()
