@@ -8,6 +8,7 @@ Host-side mirror of the reference interface for this path (same names, argument 
 * ``sampling(mu, logVar)``                 <- src/module/function.py:35-38
 * ``voxelPrecisionRecall(xTarget, xPred, prob)``  <- src/module/function.py:100-115
 * ``Darknet19(...)`` / ``head2D(...)``     <- src/net_core/darknet.py:96-133,149-168 (image encoder, encoder2d.py)
+* ``encoder3D(structure)``                 <- src/net_core/autoencoder3D.py:72-102 (voxel encoder, encoder3d.py)
 * ``anytime_eval(...)`` / ``getEval(...)`` <- the imputation + decode + score sequence of nolbo.py:1449-1528 with the
   K-sample mean of nolbo_test.py:167-177
 
@@ -28,10 +29,11 @@ import numpy as np
 from . import _capi, presets
 from ._capi import FILL, VOXELS
 from .encoder2d import Darknet19, Encoder2D, head2D, image_encoder
+from .encoder3d import Encoder3D, encoder3D
 
 __all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'voxelPrecisionRecallSweep', 'binary_loss',
            'anytime_eval', 'anytime_eval_host', 'impute', 'getEval', 'pack_targets', 'iou_from_counts', 'shard_range',
-           'allreduce_counts', 'Darknet19', 'head2D', 'image_encoder', 'Encoder2D', 'getEvalImages']
+           'allreduce_counts', 'Darknet19', 'head2D', 'image_encoder', 'Encoder2D', 'getEvalImages', 'encoder3D', 'Encoder3D', 'getEvalVoxels']
 
 
 def _torch():
@@ -525,6 +527,20 @@ def getEvalImages(encoder: Encoder2D, decoder: Decoder3D, inputs, category_vecto
     output_images, category_list)`` with RGB crops [B,H,W,3] in [0,1]; the encoder (Darknet19 + head2D, one handle from
     ``image_encoder``) produces mean / clipped logvar / z on the GPU (nolbo.py:869-875), then the latent-space
     ``getEval`` above runs unchanged.  Returns the same 10-tuple."""
+    if training:
+        raise NotImplementedError('inference only')
+    input_images, output_images, category_list = inputs
+    _, _, z = encoder.encode(input_images, decoder.input_dim, seed=seed ^ 0x656E63)
+    return getEval(decoder, (z, output_images, category_list), category_vectors, missing_prob=missing_prob, K=K,
+                   seed=seed, mask=mask, rng=rng)
+
+
+def getEvalVoxels(encoder: Encoder3D, decoder: Decoder3D, inputs, category_vectors, training: bool = False,
+                  missing_prob: float = 0.0, K: int = 1, seed: int = 0, mask=None,
+                  rng: np.random.Generator | None = None):
+    """``nolboSingleObject_modelnet_category_VAE.getEval`` (nolbo.py:1449-1528) end to end from voxel grids:
+    ``inputs = (input_images, output_images, category_list)`` with ``input_images`` [B,64,64,64,1]; the voxel encoder
+    produces mean / clipped logvar / z on the GPU (nolbo.py:1463-1470), then the latent-space ``getEval`` runs."""
     if training:
         raise NotImplementedError('inference only')
     input_images, output_images, category_list = inputs

@@ -43,6 +43,16 @@ class Enc2dDesc(C.Structure):
                 ('max_batch', C.c_int32), ('operand_dtype', C.c_int32)]
 
 
+class Enc3dDesc(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('in_grid', C.c_int32), ('num_layers', C.c_int32),
+                ('filters', C.c_int32 * A3D_MAX_LAYERS), ('ksizes', C.c_int32 * A3D_MAX_LAYERS),
+                ('strides', C.c_int32 * A3D_MAX_LAYERS), ('final_pool', C.c_int32), ('activation', C.c_int32),
+                ('final_activation', C.c_int32), ('device', C.c_int32), ('max_batch', C.c_int32),
+                ('operand_dtype', C.c_int32)]
+
+
+POOL = {'None': 0, None: 0, 'average': 1, 'max': 2}
+
 # name -> (restype, argtypes); must list every symbol include/a3d.h declares (tests check this against the header)
 SIGNATURES = {
     'a3d_create': (C.c_int, [C.POINTER(Desc), C.POINTER(C.c_void_p)]),
@@ -87,6 +97,18 @@ SIGNATURES = {
     'a3d_enc2d_debug_read_layer': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]),
     'a3d_enc2d_launch_count': (C.c_int64, [C.c_void_p]),
     'a3d_enc2d_workspace_bytes': (C.c_size_t, [C.c_void_p]),
+    'a3d_enc3d_create': (C.c_int, [C.POINTER(Enc3dDesc), C.POINTER(C.c_void_p)]),
+    'a3d_enc3d_destroy': (None, [C.c_void_p]),
+    'a3d_enc3d_num_weights': (C.c_int, [C.c_void_p]),
+    'a3d_enc3d_weight_numel': (C.c_int64, [C.c_void_p, C.c_int]),
+    'a3d_enc3d_set_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'a3d_enc3d_get_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'a3d_enc3d_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'a3d_enc3d_split_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int,
+                                         C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'a3d_enc3d_debug_read_layer': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]),
+    'a3d_enc3d_launch_count': (C.c_int64, [C.c_void_p]),
+    'a3d_enc3d_workspace_bytes': (C.c_size_t, [C.c_void_p]),
     'a3d_crc32c': (C.c_uint32, [C.c_void_p, C.c_size_t, C.c_uint32]),
     'a3d_last_error': (C.c_char_p, []),
     'a3d_abi_version': (C.c_int, []),

@@ -195,7 +195,20 @@ split_sample_kernel(const float* __restrict__ enc_out, int64_t n, int D, int out
   }
 }
 
+__global__ void __launch_bounds__(256) sigmoid_kernel(float* __restrict__ x, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] = 1.f / (1.f + __expf(-x[i]));
+}
+
 }  // namespace
+
+int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return A3D_OK;
+  sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
+  A3D_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return A3D_OK;
+}
 
 int launch_conv2d_first_pool(const float* in, const float* w27x32, const float* scale, const float* shift, void* out,
                              int64_t n, int H, int W, int cout_pad, int fmt, int act, cudaStream_t st,

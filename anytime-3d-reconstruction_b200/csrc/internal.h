@@ -120,6 +120,25 @@ int launch_split_sample(const float* enc_out, int64_t n, int D, int out_stride, 
                         uint64_t seed, uint64_t obj_offset, float* mean, float* logvar, float* z, cudaStream_t st,
                         int64_t* launches);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Voxel encoder (encoder3D, src/net_core/autoencoder3D.py:72-102); kernels in conv3d_tc.cu
+struct Conv3dGeom {
+  int G = 0;                    // OUTPUT grid (cubic)
+  int stride = 1;               // 1 or 2; 'same' with k = 4 -> pad_before = 1
+  int lw = 0, lh = 0, ld = 0;   // log2 of the output brick; nt = 128 >> (lw + lh + ld) objects per tile
+  int tiles_w = 0, tiles_h = 0, tiles_d = 0;
+  int m_tiles = 0, n_tiles = 0;
+  int cin_chunks = 0, cout_pad = 0, cout_real = 0;
+  int n_objects = 0;
+};
+int launch_conv3d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
+                     const float* shift, const Conv3dGeom& g, int bn, int fmt, int act, bool out_f32, int num_sms,
+                     cudaStream_t st, int64_t* launches);
+// first layer: fp32 grid [n, Gin^3] -> 16-bit [n, (Gin/2)^3, 64]; w64x64 = 16-bit [co][tap]
+int launch_conv3d_first_tc(const float* in, const void* w64x64, const float* scale, const float* shift, void* out,
+                           int64_t n, int Gin, int fmt, int act, int num_sms, cudaStream_t st, int64_t* launches);
+int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st, int64_t* launches);
+
 size_t convt_tc_smem_bytes(int cin, int cout, int win);
 
 }  // namespace a3d

@@ -13,6 +13,17 @@ MODELNET_DECODER = {
 }
 # test_pascal_VAE_dr.py:196-205 (latent dim 16)
 PASCAL_DECODER = dict(MODELNET_DECODER, input_dim=16)
+# test_modelnet_VAE_dr.py:172-181 (voxel encoder of the ModelNet VAE, latent dim 64 -> 2 * 64 output channels)
+MODELNET_ENCODER = {
+    'name': 'encoder3D',
+    'input_shape': [64, 64, 64, 1],
+    'filter_num_list': [64, 128, 256, 512, 128],
+    'filter_size_list': [4, 4, 4, 4, 4],
+    'strides_list': [2, 2, 2, 2, 1],
+    'final_pool': 'average',
+    'activation': 'elu',
+    'final_activation': 'None',
+}
 # test_pascal_VAE_dr.py:186-195 (encoder backbone / head of the Pascal3D VAE; head built with last_pooling='max',
 # src/module/nolbo.py:778-783)
 PASCAL_ENCODER_BACKBONE = {'name': 'nolbo_backbone', 'z_dim': 16, 'activation': 'elu'}

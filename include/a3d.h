@@ -214,6 +214,50 @@ int a3d_enc2d_debug_read_layer(a3d_enc2d* h, int layer, int64_t n, float* host, 
 int64_t a3d_enc2d_launch_count(const a3d_enc2d* h);
 size_t a3d_enc2d_workspace_bytes(const a3d_enc2d* h);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Voxel encoder: encoder3D(structure), src/net_core/autoencoder3D.py:72-102 -- Conv3D(k4,
+ * strides 2, 'same', no bias) + BN + activation x (L-1), a bare Conv3D(k4, strides 1, 'same'), reduce_mean / reduce_max
+ * over the grid, optional sigmoid.  Called as self._encoder(voxels, training=False) at src/module/nolbo.py:1463.
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { A3D_POOL_NONE = 0, A3D_POOL_AVERAGE = 1, A3D_POOL_MAX = 2 };
+
+/* Mirrors the `structure` dict of encoder3D(structure), autoencoder3D.py:73-80. */
+typedef struct {
+  int32_t abi_version;               /* A3D_ABI_VERSION */
+  int32_t in_grid;                   /* structure['input_shape'][0] (cubic, one channel): 64 */
+  int32_t num_layers;                /* len(filter_num_list) */
+  int32_t filters[A3D_MAX_LAYERS];   /* structure['filter_num_list'] */
+  int32_t ksizes[A3D_MAX_LAYERS];    /* structure['filter_size_list'] */
+  int32_t strides[A3D_MAX_LAYERS];   /* structure['strides_list'] */
+  int32_t final_pool;                /* A3D_POOL_*   (structure['final_pool']) */
+  int32_t activation;                /* A3D_ACT_*    (structure['activation']; 'lrelu' = LeakyReLU() = slope 0.3) */
+  int32_t final_activation;          /* A3D_FINAL_*  (structure['final_activation']) */
+  int32_t device;
+  int32_t max_batch;                 /* objects resident in the arena at once */
+  int32_t operand_dtype;             /* A3D_DTYPE_* */
+} a3d_enc3d_desc;
+
+typedef struct a3d_enc3d a3d_enc3d;
+
+int a3d_enc3d_create(const a3d_enc3d_desc* desc, a3d_enc3d** out);
+void a3d_enc3d_destroy(a3d_enc3d* h);
+/* Keras get_weights() order: per conv3DEnc kernel [kd,kh,kw,Cin,Cout], gamma, beta, moving_mean, moving_variance; last: kernel. */
+int a3d_enc3d_num_weights(const a3d_enc3d* h);
+int64_t a3d_enc3d_weight_numel(const a3d_enc3d* h, int index);
+int a3d_enc3d_set_weight(a3d_enc3d* h, int index, const float* host, size_t nbytes);
+int a3d_enc3d_get_weight(const a3d_enc3d* h, int index, float* host, size_t nbytes);
+/* encoder(voxels, training=False): voxels_dev [n, G, G, G, 1] fp32 on the device -> out_dev fp32 [n, filters[-1]]
+ * ([n, g, g, g, filters[-1]] when final_pool is A3D_POOL_NONE).  Asynchronous on `stream`. */
+int a3d_enc3d_forward(a3d_enc3d* h, const float* voxels_dev, int64_t n, float* out_dev, void* stream);
+/* same contract as a3d_enc2d_split_sample (src/module/nolbo.py:1464-1470) */
+int a3d_enc3d_split_sample(a3d_enc3d* h, const float* enc_out_dev, int64_t n, int D, int out_stride, float clip,
+                           int seed_enable, uint64_t seed, uint64_t obj_offset, float* mean_dev, float* logvar_dev,
+                           float* z_dev, void* stream);
+/* Diagnostics: hidden layer `layer` (0 .. num_layers-2, NDHWC, after BN + activation) of the most recent chunk as fp32. */
+int a3d_enc3d_debug_read_layer(a3d_enc3d* h, int layer, int64_t n, float* host, size_t nbytes);
+int64_t a3d_enc3d_launch_count(const a3d_enc3d* h);
+size_t a3d_enc3d_workspace_bytes(const a3d_enc3d* h);
+
 /* Host utility for the TensorFlow-checkpoint reader (anytime-3d-reconstruction_b200/tf_checkpoint.py; reference weights
  * are Keras save_weights bundles, src/module/nolbo.py:1568-1592): CRC-32C (Castagnoli) of `n` bytes, continuing from
  * `crc` (0 to start).  Pure host code, no device needed. */
