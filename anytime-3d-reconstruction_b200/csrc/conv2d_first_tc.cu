@@ -113,7 +113,6 @@ conv2d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
     phase ^= 1u;
     ptx::tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int64_t p = ((int64_t)img * Hq + hq) * Wq + wq;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t acc[4][16];
@@ -135,13 +134,28 @@ conv2d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
         }
         o[i] = pack2<FMT>(y[0], y[1]);
       }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(out + p * g.cout_pad + half * 16);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
+      // stage the pooled 64-byte row in the (now free) first A tile, same 64-byte XOR swizzle
+      *reinterpret_cast<uint4*>(&sA[0][tid * 64 + (((half * 2) ^ sw) << 4)]) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(&sA[0][tid * 64 + (((half * 2 + 1) ^ sw) << 4)]) = make_uint4(o[4], o[5], o[6], o[7]);
     }
     ptx::tc_fence_before();
+    __syncwarp();
+    {
+      // coalesced write-out: 8 rows x 64 B per store instruction (full sectors) instead of 16 B per lane per row
+      const int lane = tid & 31;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = warp * 32 + 8 * j + (lane >> 2), ch = lane & 3;
+        const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1), rni = rr >> (g.lw + g.lh);
+        const int rimg = (nb << (7 - g.lw - g.lh)) + rni;
+        const uint4 q = *reinterpret_cast<const uint4*>(&sA[0][rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4)]);
+        if (rimg < g.n_images) {
+          const int64_t rp = ((int64_t)rimg * Hq + (th << g.lh) + rhi) * Wq + (tw << g.lw) + rwi;
+          *reinterpret_cast<uint4*>(out + rp * g.cout_pad + ch * 8) = q;
+        }
+      }
+    }
+    __syncwarp();   // the next tile's A rows of this warp overwrite the staging rows it just read
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -37,7 +37,8 @@ struct Cfg {
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGES = KC == 32 ? 12 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + NUM_BARS * 8 + 16;
+  static constexpr int STAGING_BYTES = kEpiWarps * 32 * 64;   // 2 KB per epilogue warp: 32 rows x 32 columns x 16 bit
+  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + NUM_BARS * 8 + 16;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
@@ -70,7 +71,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::STAGES * C::B_BYTES);
+  uint8_t* smem_stage = smem_b + C::STAGES * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + C::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = full + C::STAGES;
   uint64_t* t_full = empty + C::STAGES;
@@ -179,6 +181,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const bool row_ok = img < g.n_images;
       const int64_t p = MODE == 2 ? ((int64_t)img * (g.H >> 1) + (ph >> 1)) * (g.W >> 1) + (pw >> 1)
                                   : ((int64_t)img * g.H + ph) * g.W + pw;
+      int64_t prow[4];   // MODE 0: pixel index of the 4 rows this lane writes out (8 * j + lane / 4), -1 if past the batch
+      if constexpr (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = quarter * 32 + 8 * j + (lane >> 2);
+          const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1), rni = rr >> (g.lw + g.lh);
+          const int rimg = (nb << (7 - g.lw - g.lh)) + rni;
+          prow[j] = rimg < g.n_images ? ((int64_t)rimg * g.H + (th << g.lh) + rhi) * g.W + (tw << g.lw) + rwi : -1;
+        }
+      }
 #pragma unroll 1
       for (int gi = 0; gi < GROUPS; ++gi) {
         const int co0 = nt * BN + chalf * CW + gi * 32;
@@ -245,11 +257,22 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0);
+          // coalesced write-out through a per-warp swizzled staging tile (32 rows x 64 B): every store instruction
+          // then covers 8 rows x 64 contiguous bytes (full sectors) instead of 16 bytes per lane in 32 different lines
+          uint8_t* stg = smem_stage + e * 2048;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          for (int c4 = 0; c4 < 4; ++c4)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + (lane >> 2), ch = lane & 3;
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+            if (prow[j] >= 0)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + prow[j] * g.cout_pad + co0 + ch * 8) = q;
           }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();

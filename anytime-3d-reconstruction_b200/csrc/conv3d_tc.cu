@@ -30,7 +30,8 @@ struct Cfg3 {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + NUM_BARS * 8 + 16;
+  static constexpr int STAGING_BYTES = kEpiWarps * 32 * 64;   // 2 KB per epilogue warp: 32 rows x 32 columns x 16 bit
+  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + NUM_BARS * 8 + 16;
 };
 
 // MODE 0: 16-bit [voxels, cout_pad]; 1: fp32 [voxels, cout_real] (final conv, feeds the global pool)
@@ -46,7 +47,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::STAGES * C::B_BYTES);
+  uint8_t* smem_stage = smem_b + C::STAGES * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + C::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = full + C::STAGES;
   uint64_t* t_full = empty + C::STAGES;
@@ -153,6 +155,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const int ow = (tw << g.lw) + wi, oh = (th << g.lh) + hi, od = (td << g.ld) + di;
       const bool row_ok = obj < g.n_objects;
       const int64_t p = (((int64_t)obj * g.G + od) * g.G + oh) * g.G + ow;
+      int64_t prow[4];   // MODE 0: voxel index of the 4 rows this lane writes out (8 * j + lane / 4), -1 if past the batch
+      if constexpr (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = quarter * 32 + 8 * j + (lane >> 2);
+          const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1);
+          const int rdi = (rr >> (g.lw + g.lh)) & ((1 << g.ld) - 1), rni = rr >> (g.lw + g.lh + g.ld);
+          const int robj = (nb << (7 - g.lw - g.lh - g.ld)) + rni;
+          prow[j] = robj < g.n_objects
+                        ? (((int64_t)robj * g.G + (td << g.ld) + rdi) * g.G + (th << g.lh) + rhi) * g.G + (tw << g.lw) + rwi
+                        : -1;
+        }
+      }
 #pragma unroll 1
       for (int gi = 0; gi < GROUPS; ++gi) {
         const int co0 = nt * BN + cgrp * CW + gi * 32;
@@ -190,11 +205,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + p * g.cout_pad + co0);
+          // coalesced write-out through a per-warp swizzled staging tile (32 rows x 64 B): every store instruction
+          // then covers 8 rows x 64 contiguous bytes (full sectors) instead of 16 bytes per lane in 32 different lines
+          uint8_t* stg = smem_stage + e * 2048;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          for (int c4 = 0; c4 < 4; ++c4)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + (lane >> 2), ch = lane & 3;
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+            if (prow[j] >= 0)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + prow[j] * g.cout_pad + co0 + ch * 8) = q;
           }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();
@@ -283,8 +309,8 @@ conv3d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
     phase ^= 1u;
     ptx::tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int64_t p = (((int64_t)obj * G + od) * G + oh) * G + ow;
-    uint4* dst = reinterpret_cast<uint4*>(out + p * 64);
+    // the MMAs have completed: the A tile is free and becomes the output staging buffer (row tid = voxel tid, 128 bytes,
+    // same XOR swizzle), so that the global stores below are full 512-byte runs instead of 16 bytes per lane per row
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t v[32];
@@ -299,9 +325,23 @@ conv3d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
                           activate<ACT>(fmaf(__uint_as_float(v[2 * i + 1]), ss[c + 1], sh[c + 1])));
       }
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) dst[half * 4 + c4] = make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+      for (int c4 = 0; c4 < 4; ++c4)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + (((half * 4 + c4) ^ (tid & 7)) << 4)) =
+            make_uint4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
     }
     ptx::tc_fence_before();
+    __syncwarp();
+    {
+      const int lane = tid & 31;
+      const int64_t tile_p = (((int64_t)obj * G + od) * G + (th << 3)) * G + (tw << 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int rr = warp * 32 + 4 * j + (lane >> 3), ch = lane & 7;   // 4 rows x 128 B = 512 contiguous bytes
+        const uint4 q = *reinterpret_cast<const uint4*>(sA + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        *reinterpret_cast<uint4*>(out + (tile_p + (int64_t)(rr >> 4) * G + (rr & 15)) * 64 + ch * 8) = q;
+      }
+    }
+    __syncwarp();   // the next tile's A rows of this warp overwrite the staging rows it just read
   }
   ptx::tc_fence_before();
   __syncthreads();
