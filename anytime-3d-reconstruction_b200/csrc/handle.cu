@@ -92,6 +92,9 @@ struct a3d_handle {
   float* d_w5 = nullptr;                                                       // final kernel [tap][ci] fp32
   void* d_w5_16 = nullptr;                                                     // same, operand dtype (tcgen05 tail)
   CUtensorMap tmap_a4, tmap_w5;                                                // tail: (c,w,h,d,n) view of act[4]; W5
+  void* d_w5_pair = nullptr;                                                   // pair tail (tail_tc2.cu): [Za 32 | Zm 16 | Zp 16] rows
+  CUtensorMap tmap_a4p, tmap_w5p;                                              // pair tail: (c,h,d,n,w) view of act[4]; its W5
+  bool tail_v3 = false;                                                        // A3D_TAIL_IMPL=v3: always use tail_tc.cu
   // arena
   int64_t max_chunk = 0;
   void* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // a0..a4
@@ -361,6 +364,30 @@ int finalize_weights(a3d_handle* h) {
     r = enc(&h->tmap_w5, dt, 2, h->d_w5_16, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    // pair tail (tail_tc2.cu): B rows 0..31 = W[td,th,tap_w = pw+1] at n = (td*4+th)*2+pw; 32..47 = W[td,th,3]; 48..63 = W[td,th,0]
+    p16.assign((size_t)64 * 64, cvt16(0.f, fmt));
+    for (int td = 0; td < 4; ++td)
+      for (int th = 0; th < 4; ++th) {
+        const int q = td * 4 + th;
+        for (int ci = 0; ci < 64; ++ci) {
+          p16[(size_t)(2 * q + 0) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 1) * 64 + ci], fmt);
+          p16[(size_t)(2 * q + 1) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 2) * 64 + ci], fmt);
+          p16[(size_t)(32 + q) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 3) * 64 + ci], fmt);
+          p16[(size_t)(48 + q) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 0) * 64 + ci], fmt);
+        }
+      }
+    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_pair))) return rc;
+    cuuint64_t pd[5] = {64, 32, 32, (cuuint64_t)h->max_chunk, 32};   // (c, h, d, n, w): GEMM rows come out (w, sample, d, h)
+    cuuint64_t ps[4] = {128 * 32, 128 * 32 * 32, 128ull * 32 * 32 * 32, 128};
+    cuuint32_t pb[5] = {64, 8, 8, 2, 4};
+    r = enc(&h->tmap_a4p, dt, 5, h->act[4], pd, ps, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pair-tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    cuuint64_t wpd[2] = {64, 64};
+    cuuint32_t wpb[2] = {64, 64};
+    r = enc(&h->tmap_w5p, dt, 2, h->d_w5_pair, wpd, ws, wpb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pair-tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
   }
   h->dirty = false;
   return A3D_OK;
@@ -407,6 +434,10 @@ int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, un
   if (h->desc.impl == A3D_IMPL_SIMT)
     return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss, st,
                        &h->launches);
+  // even K (configs 2 and 5): the pair kernel reads every activation tile once instead of three times
+  if (K >= 2 && (K & 1) == 0 && !h->tail_v3 && h->max_chunk >= 2)
+    return launch_tail_pair(h->tmap_a4p, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
+                            loss, h->num_sms, st, &h->launches);
   return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss,
                         h->num_sms, st, &h->launches);
 }
@@ -500,6 +531,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
   { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = e && std::string(e) == "generic"; }
+  { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
   h->act_elems[0] = 512; h->act_elems[1] = 64 * 512; h->act_elems[2] = 512 * 256; h->act_elems[3] = 4096 * 128;
@@ -526,7 +558,7 @@ void a3d_destroy(a3d_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
-  cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16);
+  cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16); cudaFree(h->d_w5_pair);
   for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
