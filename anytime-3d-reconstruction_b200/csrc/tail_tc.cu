@@ -38,6 +38,9 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;  // 640
 constexpr int kSmem = 1024 + kPad + 2 * kAStride + kWBytes + 2 * kExD + 16 * 8 + 16;
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory"); }
+// The d-axis exchange only couples rows r and r +- 8 of one 64-row (d, h) plane group = the two epilogue warps 2j, 2j + 1:
+// a 64-thread named barrier per warp pair (ids 2..9) instead of a 512-thread barrier per sample
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
 
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -198,7 +201,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
             ex[((0 * 2 + ph) * 2 + pw) * kPos + r] = zh[3][ph][pw];
             ex[((1 * 2 + ph) * 2 + pw) * kPos + r] = zh[0][ph][pw];
           }
-        epi_sync();
+        pair_sync(e >> 1);
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph)
 #pragma unroll

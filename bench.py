@@ -346,9 +346,10 @@ def main():
                 'traffic': 30.17e9, 'traffic_unit': 'bytes per launch (ncu, profiles/r01_l4_ws2cta_ncu_full.txt)',
                 'peak_source': f'{src} sustained bf16', 'stage_ms': stage,
                 'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12,
-                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_tc_kernel (final ConvT + sigmoid + K-mean + threshold + counts)',
+                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_pair_kernel (final ConvT + sigmoid + K-mean + threshold + counts)',
                                'achieved': tail_gbs, 'peak': hpeak, 'unit': 'GB/s', 'frac': tail_gbs / hpeak,
-                               'traffic': 17.70e9, 'algorithmic_bytes_per_launch': tail_bytes}}
+                               'traffic': 17.19e9,   # dram bytes of one launch, profiles/r01_tail_pair_ncu_full.txt
+                               'algorithmic_bytes_per_launch': tail_bytes}}
 
     aux = None
     if rank == 0:
