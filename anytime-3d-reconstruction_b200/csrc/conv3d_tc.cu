@@ -79,10 +79,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================================================== TMA producer (converged warp, elected-lane issue)
-    int s = 0;
-    uint32_t ph = 0;
+  if (warp == 0 || warp == 3) {
+    // ===================================================== TMA producers: warp 0 feeds the even K steps, warp 3 the odd ones
+    // (see conv2d_tc.cu: one warp's ~550 clk of dependent issue work per K step starves the MMA warp)
+    const int par = warp == 3 ? 1 : 0;
+    int s = par;
+    uint32_t ph = 0, cnt = 0;
+    static_assert(C::STAGES % 2 == 0, "two producer warps need an even stage count");
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int nt = u % g.n_tiles, mt = u / g.n_tiles;
       const int tb = mt % tiles_per_obj, nb = mt / tiles_per_obj;
@@ -93,7 +96,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       for (int kd = 0; kd < 4; ++kd)
         for (int kh = 0; kh < 4; ++kh)
           for (int kw = 0; kw < 4; ++kw) {
-            for (int kc = 0; kc < g.cin_chunks; ++kc) {
+            for (int kc = 0; kc < g.cin_chunks; ++kc, ++cnt) {
+              if ((cnt & 1u) != (uint32_t)par) continue;
               ptx::mbar_wait(&empty[s], ph ^ 1);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(&full[s], A_BYTES + C::B_BYTES);
@@ -101,7 +105,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
                 ptx::tma_load_2d(smem_b + s * C::B_BYTES, &tmap_wgt, &full[s], kc * 64, brow);
               }
               __syncwarp();
-              if (++s == C::STAGES) { s = 0; ph ^= 1; }
+              s += 2;
+              if (s >= C::STAGES) { s -= C::STAGES; ph ^= 1; }
             }
             brow += g.cout_pad;
           }

@@ -67,6 +67,7 @@ struct a3d_enc2d {
   int64_t launches = 0;
   int64_t last_n = 0;
   int sticky = 0;
+  bool no_rh = false;         // A3D_ENC_RH=0: disable the resident-weight conv variant (cross-check)
   bool first_simt = false;    // A3D_ENC_FIRST=simt: CUDA-core image layer (diagnostic cross-check of the tensor-core one)
 };
 
@@ -83,7 +84,7 @@ int sticky(a3d_enc2d* h, int rc) {
 }
 
 // brick of the conv M tile: contiguous pixels for plain convs, at most 16 wide (and >= 2 high) when a pool is fused
-void choose_brick(Op2d& op) {
+void choose_brick(Op2d& op, bool rh_ok) {
   const int W = op.W, H = op.H;
   int wt = op.pool ? (W < 16 ? W : 16) : (W < 128 ? W : 128);
   int ht = 128 / wt;
@@ -98,6 +99,13 @@ void choose_brick(Op2d& op) {
   g.cout_pad = op.cout_pad;
   g.cout_real = op.cout;
   g.n_tiles = op.cout_pad / op.bn_tile;
+  // resident-weight variant (conv2d_tc.cu, CfgRH): shallow 3 x 3 layers whose nine weight tiles fit in shared memory
+  const bool rh_shape = (g.kc == 32 && op.bn_tile == 64 && op.cout_pad == 64) || (g.kc == 64 && op.bn_tile == 128 && op.cout_pad == 128);
+  if (rh_ok && op.ksize == 3 && g.cin_chunks == 1 && g.n_tiles == 1 && rh_shape && !op.out_f32 && W >= 16 && H >= 8) {
+    g.rh = 1;
+    g.lw = 4; g.lh = 3;                       // 16 x 8 brick (also for the plain 16-bit mode)
+    g.tiles_w = W / 16; g.tiles_h = H / 8;
+  }
 }
 
 int build_plan(a3d_enc2d* h) {
@@ -145,7 +153,7 @@ int build_plan(a3d_enc2d* h) {
         op.out_f32 = next_gpool;
         if (op.pool && ((H & 1) || (W & 1))) { set_error("layer %d: max-pool on an odd size", li); return A3D_ERR_INVALID; }
         op.bn_tile = op.cin_pad % 64 == 0 ? conv2d_tc_bn(op.cout_pad) : 64;   // 32-channel K steps: N tile 64 only
-        choose_brick(op);
+        choose_brick(op, !h->no_rh);
         if (op.pool && op.g.lh < 1) { set_error("layer %d: fused pool needs H >= 2", li); return A3D_ERR_INVALID; }
       }
       Buf2d b;
@@ -227,6 +235,7 @@ int make_maps(a3d_enc2d* h, Op2d& op) {
   const cuuint32_t kc = (cuuint32_t)op.g.kc;
   const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint32_t box[4] = {kc, 1u << op.g.lw, 1u << op.g.lh, 128u >> (op.g.lw + op.g.lh)};
+  if (op.g.rh) box[2] = 10;   // haloed box: 16 x (8 + 2) pixels, one load per dx serves the three dy taps
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(&op.tmap_act, dt, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -345,6 +354,7 @@ int a3d_enc2d_create(const a3d_enc2d_desc* d, a3d_enc2d** out) {
   if (d->max_batch < 1) { set_error("max_batch must be >= 1"); return A3D_ERR_INVALID; }
   a3d_enc2d* h = new a3d_enc2d();
   h->desc = *d;
+  { const char* e = getenv("A3D_ENC_RH"); h->no_rh = e && std::string(e) == "0"; }
   int rc = build_plan(h);   // validates the structure before any device work (usable without a GPU for error paths)
   if (rc) { delete h; return rc; }
   int ndev = 0;

@@ -37,7 +37,6 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // 640
 constexpr int kSmem = 1024 + kPad + 2 * kAStride + kWBytes + 2 * kExD + 16 * 8 + 16;
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory"); }
 // The d-axis exchange only couples rows r and r +- 8 of one 64-row (d, h) plane group = the two epilogue warps 2j, 2j + 1:
 // a 64-thread named barrier per warp pair (ids 2..9) instead of a 512-thread barrier per sample
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
