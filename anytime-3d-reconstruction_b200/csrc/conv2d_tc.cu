@@ -50,11 +50,13 @@ struct Cfg {
 // Operand bytes per 128-pixel tile: 288 KB -> 60 KB (64 -> 128 channels), 108 KB -> 30 KB (32 -> 64 channels).
 template <int BN, int KC, int MODE>
 struct CfgRH {
-  static constexpr int HALO_ROWS = 16 * 10;
+  // MODE 3 (pool through four accumulators): GEMM rows are POOLED pixels; a stage is one element-strided box of
+  // 16 x 9 pooled positions (one of 4 x-offsets x 2 row parities), two row-shifted views each
+  static constexpr int HALO_ROWS = MODE == 3 ? 16 * 9 : 16 * 10;
   static constexpr int A_BYTES = HALO_ROWS * KC * 2;
   static constexpr int W_TILE = BN * KC * 2;
   static constexpr int RES_BYTES = 9 * W_TILE;
-  static constexpr int STAGING_BYTES = MODE == 0 ? kEpiWarps * 32 * 64 : 0;
+  static constexpr int STAGING_BYTES = (MODE == 0 || MODE == 3) ? kEpiWarps * 32 * 64 : 0;
   // 128-wide N tile: 144 KB of weights are resident, so the plain 16-bit mode (which needs the 32 KB store staging) keeps
   // two 20 KB activation stages, the pooled mode four
   static constexpr int STAGES = KC == 32 ? 8 : (MODE == 0 ? 2 : 4);
@@ -79,7 +81,9 @@ __device__ __forceinline__ float act2d(float v) {
 }
 
 // MODE 0: 16-bit [pixels, cout_pad]; 1: fp32 [pixels, cout_real] (final head conv; feeds the global pool);
-// 2: 16-bit with the 2 x 2 max-pool fused, [n, H/2, W/2, cout_pad]
+// 2: 16-bit with the 2 x 2 max-pool fused, [n, H/2, W/2, cout_pad] (pool by warp shuffles);
+// 3 (RH, BN = 64 only): same output as 2, but GEMM rows are pooled pixels and each of the four pool-window positions has its
+//    own accumulator (4 x 64 TMEM columns per buffer): the pool is a per-thread max, no shuffles
 template <int BN, int KC, int FMT, int ACT, int MODE, bool RH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
@@ -93,7 +97,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   constexpr int STAGES = RH ? R::STAGES : C::STAGES;
   constexpr int B_REGION = RH ? R::RES_BYTES : C::STAGES * C::B_BYTES;     // resident weight tiles / per-stage weight tiles
   constexpr int STAGING = RH ? R::STAGING_BYTES : C::STAGING_BYTES;
-  constexpr bool SS_SMEM = BN <= 128 && MODE != 2;   // scale / shift of a warp's 32 columns live in shared memory (LDS broadcast) instead
+  constexpr bool SS_SMEM = BN <= 128 && MODE != 2;
+  constexpr int TBUF = MODE == 3 ? 4 * BN : BN;   // TMEM columns per accumulator buffer   // scale / shift of a warp's 32 columns live in shared memory (LDS broadcast) instead
                                         // of 16 LDG.128 per tile behind the store queue (stall_lg / long_scoreboard); not in
                                         // the pooled mode, whose shuffles already load the MIO pipe (measured: slower)
   constexpr int SS_BYTES = SS_SMEM ? (RH ? R::SS_BYTES : C::SS_BYTES) : 0;
@@ -154,6 +159,24 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         }
         __syncwarp();
       }
+      if constexpr (MODE == 3) {
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+          const int tw = u % g.tiles_w, th = (u / g.tiles_w) % g.tiles_h, nb = u / (g.tiles_w * g.tiles_h);
+          const int w0 = (tw << 5) - 1, h0 = (th << 4) - 1;       // conv-pixel origin of the 16 x 8 pooled brick, minus the pad
+          for (int box = 0; box < 8; ++box, ++cnt) {               // box = x-offset (0..3) * 2 + row parity
+            if ((cnt & 1u) != (uint32_t)par) continue;
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(&full[s], A_BYTES);
+              // element strides (1, 2, 2, 1): pixels (w0 + xo + 2*i, h0 + yp + 2*j), i < 16, j < 9
+              tma_load_4d(smem_a + s * A_BYTES, &tmap_act, &full[s], 0, w0 + (box >> 1), h0 + (box & 1), nb);
+            }
+            __syncwarp();
+            s += 2;
+            if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+          }
+        }
+      } else
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const int tw = u % g.tiles_w, th = (u / g.tiles_w) % g.tiles_h, nb = u / (g.tiles_w * g.tiles_h);
         const int w0 = (tw << 4) - 1, h0 = (th << 3) - 1;
@@ -206,8 +229,45 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + buf * BN;
-      if constexpr (RH) {
+      const uint32_t tacc = tmem_base + buf * TBUF;
+      if constexpr (RH && MODE == 3) {
+        constexpr uint32_t DY_STEP = (16 * KC * 2) >> 4;   // one pooled row = 16 GEMM rows
+        uint32_t touched = 0;
+        for (int box = 0; box < 8; ++box) {
+          const int xo = box >> 1, yp = box & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4);
+          if (ptx::elect_one()) {
+            for (int sh = 0; sh < 2; ++sh) {
+              const int yo = yp + 2 * sh;                     // row offset of this view inside the 4 x 4 patch
+              for (int py = 0; py < 2; ++py) {
+                const int dy = yo - py;
+                if (dy < 0 || dy > 2) continue;
+                for (int px = 0; px < 2; ++px) {
+                  const int dx = xo - px;
+                  if (dx < 0 || dx > 2) continue;
+                  const int a = py * 2 + px;                  // accumulator of pool-window position (py, px)
+                  const uint32_t b_lo = b_lo0 + (dy * 3 + dx) * (R::W_TILE >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < KC / 16; ++kk) {
+                    const uint32_t acc = ((touched >> a) & 1u) | (uint32_t)(kk != 0);
+                    if constexpr (KC == 64)
+                      ptx::umma_f16<1>(tacc + a * BN, ptx::sw128_desc(a_lo + sh * DY_STEP + kk * 2), ptx::sw128_desc(b_lo + kk * 2), idesc, acc);
+                    else
+                      ptx::umma_f16<1>(tacc + a * BN, ptx::sw64_desc(a_lo + sh * DY_STEP + kk * 2), ptx::sw64_desc(b_lo + kk * 2), idesc, acc);
+                  }
+                  touched |= 1u << a;
+                }
+              }
+            }
+            ptx::umma_commit<1>(&empty[s]);
+            if (box == 7) ptx::umma_commit<1>(&t_full[buf]);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      } else if constexpr (RH) {
         constexpr uint32_t DY_STEP = (16 * KC * 2) >> 4;   // one image row of the haloed box = 16 GEMM rows
         for (int dx = 0; dx < 3; ++dx) {
           ptx::mbar_wait(&full[s], ph);
@@ -265,13 +325,14 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + lane_base + buf * BN + chalf * CW;
+      const uint32_t tacc = tmem_base + lane_base + buf * TBUF + chalf * CW;
       const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, nb = mt / (g.tiles_w * g.tiles_h);
       const int r = quarter * 32 + lane;
       const int wi = r & ((1 << g.lw) - 1), hi = (r >> g.lw) & ((1 << g.lh) - 1), ni = r >> (g.lw + g.lh);
       const int img = (nb << (7 - g.lw - g.lh)) + ni;
       const int ph = (th << g.lh) + hi, pw = (tw << g.lw) + wi;
       const bool row_ok = img < g.n_images;
+      // MODE 3: (ph, pw) already are pooled coordinates (the brick tiles the pooled grid)
       const int64_t p = MODE == 2 ? ((int64_t)img * (g.H >> 1) + (ph >> 1)) * (g.W >> 1) + (pw >> 1)
                                   : ((int64_t)img * g.H + ph) * g.W + pw;
       // RH kernels have a single N tile, so the values never change and the four quarter warps of a column group may
@@ -287,22 +348,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         }
       }
       int64_t prow[4];   // MODE 0: pixel index of the 4 rows this lane writes out (8 * j + lane / 4), -1 if past the batch
-      if constexpr (MODE == 0) {
+      if constexpr (MODE == 0 || MODE == 3) {
+        const int oH = MODE == 3 ? g.H >> 1 : g.H, oW = MODE == 3 ? g.W >> 1 : g.W;   // grid the brick tiles
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int rr = quarter * 32 + 8 * j + (lane >> 2);
           const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1), rni = rr >> (g.lw + g.lh);
           const int rimg = (nb << (7 - g.lw - g.lh)) + rni;
-          prow[j] = rimg < g.n_images ? ((int64_t)rimg * g.H + (th << g.lh) + rhi) * g.W + (tw << g.lw) + rwi : -1;
+          prow[j] = rimg < g.n_images ? ((int64_t)rimg * oH + (th << g.lh) + rhi) * oW + (tw << g.lw) + rwi : -1;
         }
       }
 #pragma unroll 1
       for (int gi = 0; gi < GROUPS; ++gi) {
         const int co0 = nt * BN + chalf * CW + gi * 32;
         uint32_t v[32];
-        ptx::tmem_ld16(tacc + gi * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        ptx::tmem_ld16(tacc + gi * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        ptx::tmem_ld_wait();
+        if constexpr (MODE != 3) {
+          ptx::tmem_ld16(tacc + gi * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          ptx::tmem_ld16(tacc + gi * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          ptx::tmem_ld_wait();
+        }
         const float4* sc4 = SS_SMEM ? reinterpret_cast<const float4*>(my_ss) : reinterpret_cast<const float4*>(scale + co0);
         const float4* sh4 = SS_SMEM ? reinterpret_cast<const float4*>(my_ss + 32) : reinterpret_cast<const float4*>(shift + co0);
         auto ld4 = [&](const float4* q) -> float4 {
@@ -355,6 +419,32 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           }
         } else {
           uint32_t o[16];
+          if constexpr (MODE == 3) {
+            // four accumulators (one per pool-window position) in four BN-column blocks of this lane: the pool is a
+            // per-thread max of scale * acc, taken before the BN shift and the activation (both monotone)
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {
+              uint32_t a4[4][16];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) ptx::tmem_ld16(tacc + a * BN + gi * 32 + h16 * 16, a4[a]);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 sc = ld4(sc4 + h16 * 4 + i), sh = ld4(sh4 + h16 * 4 + i);
+                const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, t4[4] = {sh.x, sh.y, sh.z, sh.w};
+                float y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int c = 4 * i + j;
+                  const float m = fmaxf(fmaxf(__uint_as_float(a4[0][c]) * s4[j], __uint_as_float(a4[1][c]) * s4[j]),
+                                        fmaxf(__uint_as_float(a4[2][c]) * s4[j], __uint_as_float(a4[3][c]) * s4[j]));
+                  y[j] = act2d<ACT>(m + t4[j]);
+                }
+                o[h16 * 8 + 2 * i] = pack2<FMT>(y[0], y[1]);
+                o[h16 * 8 + 2 * i + 1] = pack2<FMT>(y[2], y[3]);
+              }
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 sc = ld4(sc4 + i), sh = ld4(sh4 + i);
@@ -364,6 +454,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             const float x3 = act2d<ACT>(fmaf(__uint_as_float(v[4 * i + 3]), sc.w, sh.w));
             o[2 * i] = pack2<FMT>(x0, x1);
             o[2 * i + 1] = pack2<FMT>(x2, x3);
+          }
           }
           {
           // coalesced write-out through a per-warp swizzled staging tile (32 rows x 64 B): every store instruction
@@ -422,6 +513,12 @@ int launch_fmt(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const fl
                const Conv2dGeom& g, int fmt, int act, int mode, int grid, cudaStream_t st) {
   if constexpr (RH) {   // resident-weight variant: 16-bit outputs only (plain or pooled)
     if (mode == 1) { set_error("conv2d: the resident-weight variant has no fp32 output mode"); return A3D_ERR_INVALID; }
+    if constexpr (BN == 64) {
+      if (mode == 3)
+        return fmt == A3D_DTYPE_F16 ? launch_bn<BN, KC, A3D_DTYPE_F16, 3, true>(ta, tw, out, scale, shift, g, act, grid, st)
+                                    : launch_bn<BN, KC, A3D_DTYPE_BF16, 3, true>(ta, tw, out, scale, shift, g, act, grid, st);
+    }
+    if (mode == 3) { set_error("conv2d: the four-accumulator pool is built for 64-wide N tiles only"); return A3D_ERR_INVALID; }
     if (fmt == A3D_DTYPE_F16)
       return mode == 0 ? launch_bn<BN, KC, A3D_DTYPE_F16, 0, true>(ta, tw, out, scale, shift, g, act, grid, st)
                        : launch_bn<BN, KC, A3D_DTYPE_F16, 2, true>(ta, tw, out, scale, shift, g, act, grid, st);
@@ -447,13 +544,13 @@ int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, v
                      const float* shift, const Conv2dGeom& g, int bn, int fmt, int act, bool pool, bool out_f32,
                      int num_sms, cudaStream_t st, int64_t* launches) {
   if (g.n_images <= 0) return A3D_OK;
-  if (pool && (out_f32 || g.lw > 4 || g.lh < 1 || (g.H & 1) || (g.W & 1))) {
+  if (pool && g.rh != 2 && (out_f32 || g.lw > 4 || g.lh < 1 || (g.H & 1) || (g.W & 1))) {
     set_error("conv2d: fused pool needs a brick at most 16 wide and at least 2 high on even sizes");
     return A3D_ERR_INVALID;
   }
   const int total = g.m_tiles * g.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  const int mode = out_f32 ? 1 : (pool ? 2 : 0);
+  const int mode = out_f32 ? 1 : (pool ? (g.rh == 2 ? 3 : 2) : 0);
   int rc;
   if (g.rh) {
     // resident weights + haloed activation box: 3 x 3, one Cin chunk, one N tile, 16 x 8 brick inside one image

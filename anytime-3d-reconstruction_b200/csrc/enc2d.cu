@@ -67,6 +67,7 @@ struct a3d_enc2d {
   int64_t launches = 0;
   int64_t last_n = 0;
   int sticky = 0;
+  bool no_p4 = false;         // A3D_ENC_P4=0: keep the shuffle pool in the resident-weight variant (cross-check)
   bool no_rh = false;         // A3D_ENC_RH=0: disable the resident-weight conv variant (cross-check)
   bool first_simt = false;    // A3D_ENC_FIRST=simt: CUDA-core image layer (diagnostic cross-check of the tensor-core one)
 };
@@ -84,7 +85,7 @@ int sticky(a3d_enc2d* h, int rc) {
 }
 
 // brick of the conv M tile: contiguous pixels for plain convs, at most 16 wide (and >= 2 high) when a pool is fused
-void choose_brick(Op2d& op, bool rh_ok) {
+void choose_brick(Op2d& op, bool rh_ok, bool p4_ok) {
   const int W = op.W, H = op.H;
   int wt = op.pool ? (W < 16 ? W : 16) : (W < 128 ? W : 128);
   int ht = 128 / wt;
@@ -105,6 +106,10 @@ void choose_brick(Op2d& op, bool rh_ok) {
     g.rh = 1;
     g.lw = 4; g.lh = 3;                       // 16 x 8 brick (also for the plain 16-bit mode)
     g.tiles_w = W / 16; g.tiles_h = H / 8;
+    if (op.pool && op.bn_tile == 64 && p4_ok && W >= 32 && H >= 16) {
+      g.rh = 2;                               // pool through four accumulators: the 16 x 8 brick tiles the pooled grid
+      g.tiles_w = (W / 2) / 16; g.tiles_h = (H / 2) / 8;
+    }
   }
 }
 
@@ -153,7 +158,7 @@ int build_plan(a3d_enc2d* h) {
         op.out_f32 = next_gpool;
         if (op.pool && ((H & 1) || (W & 1))) { set_error("layer %d: max-pool on an odd size", li); return A3D_ERR_INVALID; }
         op.bn_tile = op.cin_pad % 64 == 0 ? conv2d_tc_bn(op.cout_pad) : 64;   // 32-channel K steps: N tile 64 only
-        choose_brick(op, !h->no_rh);
+        choose_brick(op, !h->no_rh, !h->no_p4);
         if (op.pool && op.g.lh < 1) { set_error("layer %d: fused pool needs H >= 2", li); return A3D_ERR_INVALID; }
       }
       Buf2d b;
@@ -235,15 +240,20 @@ int make_maps(a3d_enc2d* h, Op2d& op) {
   const cuuint32_t kc = (cuuint32_t)op.g.kc;
   const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint32_t box[4] = {kc, 1u << op.g.lw, 1u << op.g.lh, 128u >> (op.g.lw + op.g.lh)};
-  if (op.g.rh) box[2] = 10;   // haloed box: 16 x (8 + 2) pixels, one load per dx serves the three dy taps
   cuuint32_t es[4] = {1, 1, 1, 1};
+  if (op.g.rh == 1) box[2] = 10;   // haloed box: 16 x (8 + 2) pixels, one load per dx serves the three dy taps
+  if (op.g.rh == 2) {              // element-strided box: every second pixel, 16 x 9 pooled positions
+    box[1] = 32; box[2] = 18; box[3] = 1;
+    es[1] = 2; es[2] = 2;
+  }
   CUresult r = enc(&op.tmap_act, dt, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder activations, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
   cuuint64_t wd[2] = {C, (cuuint64_t)op.ksize * op.ksize * op.cout_pad};
   cuuint64_t ws[1] = {C * 2};
   cuuint32_t wb[2] = {kc, (cuuint32_t)op.bn_tile};
-  r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  cuuint32_t es1[2] = {1, 1};
+  r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder weights, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
   return A3D_OK;
@@ -355,6 +365,7 @@ int a3d_enc2d_create(const a3d_enc2d_desc* d, a3d_enc2d** out) {
   a3d_enc2d* h = new a3d_enc2d();
   h->desc = *d;
   { const char* e = getenv("A3D_ENC_RH"); h->no_rh = e && std::string(e) == "0"; }
+  { const char* e = getenv("A3D_ENC_P4"); h->no_p4 = e && std::string(e) == "0"; }
   int rc = build_plan(h);   // validates the structure before any device work (usable without a GPU for error paths)
   if (rc) { delete h; return rc; }
   int ndev = 0;

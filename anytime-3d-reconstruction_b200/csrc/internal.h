@@ -97,7 +97,9 @@ struct Conv2dGeom {
   int m_tiles = 0, n_tiles = 0;
   int taps = 0, cin_chunks = 0, cout_pad = 0, cout_real = 0;
   int kc = 64;                 // channels per K step (64: SWIZZLE_128B rows, 32: SWIZZLE_64B rows)
-  int rh = 0;                  // 1: resident weights + haloed activation box (tmap_act box = (kc, 16, 10, 1))
+  int rh = 0;                  // 1: resident weights + haloed activation box (tmap_act box = (kc, 16, 10, 1));
+                               // 2: + fused pool through four accumulators: the brick tiles the POOLED grid and tmap_act
+                               //    is element-strided (box (kc, 32, 18, 1), strides (1, 2, 2, 1))
   int n_images = 0;
 };
 int conv2d_tc_bn(int cout_pad);
