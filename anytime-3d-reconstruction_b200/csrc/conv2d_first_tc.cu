@@ -62,7 +62,7 @@ conv2d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
     const int tw = tile % g.tiles_w, th = (tile / g.tiles_w) % g.tiles_h, nb = tile / (g.tiles_w * g.tiles_h);
     const int img = (nb << (7 - g.lw - g.lh)) + ni;
     const int hq = (th << g.lh) + hi, wq = (tw << g.lw) + wi;
-    const bool valid = img < g.n_images;
+    const bool valid = img < g.n_images && hq < Hq && wq < Wq;   // the power-of-two brick may overhang the pooled grid
     float patch[4][4][3];
     const float* base = in + (int64_t)img * g.H * g.W * 3;
 #pragma unroll
@@ -149,8 +149,9 @@ conv2d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
         const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1), rni = rr >> (g.lw + g.lh);
         const int rimg = (nb << (7 - g.lw - g.lh)) + rni;
         const uint4 q = *reinterpret_cast<const uint4*>(&sA[0][rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4)]);
-        if (rimg < g.n_images) {
-          const int64_t rp = ((int64_t)rimg * Hq + (th << g.lh) + rhi) * Wq + (tw << g.lw) + rwi;
+        const int rhq = (th << g.lh) + rhi, rwq = (tw << g.lw) + rwi;
+        if (rimg < g.n_images && rhq < Hq && rwq < Wq) {
+          const int64_t rp = ((int64_t)rimg * Hq + rhq) * Wq + rwq;
           *reinterpret_cast<uint4*>(out + rp * g.cout_pad + ch * 8) = q;
         }
       }
@@ -171,14 +172,12 @@ int launch_conv2d_first_tc(const float* in, const void* w32x32, const float* sca
   FirstGeom g;
   if ((H & 1) || (W & 1) || H < 2 || W < 2) { set_error("conv2d_first: needs even H, W >= 2"); return A3D_ERR_INVALID; }
   const int Wq = W / 2, Hq = H / 2;   // the brick tiles the POOLED grid
-  const int wt = Wq < 16 ? Wq : 16;
-  int ht = 128 / wt;
-  if (ht > Hq) ht = Hq;
-  int lw = 0, lh = 0;
-  while ((1 << lw) < wt) ++lw;
-  while ((1 << lh) < ht) ++lh;
+  int lw = 0, lh = 0;   // power-of-two brick of pooled pixels, at most 16 wide; it may overhang the pooled grid
+  while (lw < 4 && (2 << lw) <= Wq) ++lw;
+  while (lw + lh < 7 && (2 << lh) <= Hq) ++lh;
+  const int wt = 1 << lw, ht = 1 << lh;
   const int nt = 128 >> (lw + lh);
-  g.H = H; g.W = W; g.lw = lw; g.lh = lh; g.tiles_w = Wq / wt; g.tiles_h = Hq / ht;
+  g.H = H; g.W = W; g.lw = lw; g.lh = lh; g.tiles_w = (Wq + wt - 1) / wt; g.tiles_h = (Hq + ht - 1) / ht;
   g.total_tiles = (int)((n + nt - 1) / nt) * g.tiles_w * g.tiles_h;
   g.n_images = (int)n; g.cout_pad = cout_pad;
   const int grid = g.total_tiles < num_sms * 4 ? g.total_tiles : num_sms * 4;

@@ -331,7 +331,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const int wi = r & ((1 << g.lw) - 1), hi = (r >> g.lw) & ((1 << g.lh) - 1), ni = r >> (g.lw + g.lh);
       const int img = (nb << (7 - g.lw - g.lh)) + ni;
       const int ph = (th << g.lh) + hi, pw = (tw << g.lw) + wi;
-      const bool row_ok = img < g.n_images;
+      // bricks are powers of two and may overhang the image (sizes that are not powers of two): overhanging rows read
+      // zeros through TMA and are never stored
+      const bool row_ok = img < g.n_images && pw < (MODE == 3 ? g.W >> 1 : g.W) && ph < (MODE == 3 ? g.H >> 1 : g.H);
       // MODE 3: (ph, pw) already are pooled coordinates (the brick tiles the pooled grid)
       const int64_t p = MODE == 2 ? ((int64_t)img * (g.H >> 1) + (ph >> 1)) * (g.W >> 1) + (pw >> 1)
                                   : ((int64_t)img * g.H + ph) * g.W + pw;
@@ -355,7 +357,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           const int rr = quarter * 32 + 8 * j + (lane >> 2);
           const int rwi = rr & ((1 << g.lw) - 1), rhi = (rr >> g.lw) & ((1 << g.lh) - 1), rni = rr >> (g.lw + g.lh);
           const int rimg = (nb << (7 - g.lw - g.lh)) + rni;
-          prow[j] = rimg < g.n_images ? ((int64_t)rimg * oH + (th << g.lh) + rhi) * oW + (tw << g.lw) + rwi : -1;
+          const int rph = (th << g.lh) + rhi, rpw = (tw << g.lw) + rwi;
+          prow[j] = (rimg < g.n_images && rph < oH && rpw < oW) ? ((int64_t)rimg * oH + rph) * oW + rpw : -1;
         }
       }
 #pragma unroll 1

@@ -44,8 +44,6 @@ struct Buf2d {
   void* ptr = nullptr;
 };
 
-inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
-inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
@@ -87,13 +85,17 @@ int sticky(a3d_enc2d* h, int rc) {
 // brick of the conv M tile: contiguous pixels for plain convs, at most 16 wide (and >= 2 high) when a pool is fused
 void choose_brick(Op2d& op, bool rh_ok, bool p4_ok) {
   const int W = op.W, H = op.H;
-  int wt = op.pool ? (W < 16 ? W : 16) : (W < 128 ? W : 128);
-  int ht = 128 / wt;
-  if (ht > H) ht = H;
+  // power-of-two brick (largest that fits, <= 16 wide when a pool is fused); it may overhang images whose size is not a
+  // power of two: overhanging rows read zeros through TMA and are masked in the epilogue
+  const int wcap = op.pool ? 16 : 128;
+  int lw = 0, lh = 0;
+  while ((2 << lw) <= W && (2 << lw) <= wcap) ++lw;
+  while (lw + lh < 7 && (2 << lh) <= H) ++lh;
+  const int wt = 1 << lw, ht = 1 << lh;
   Conv2dGeom& g = op.g;
   g.H = H; g.W = W;
-  g.lw = ilog2(wt); g.lh = ilog2(ht);
-  g.tiles_w = W / wt; g.tiles_h = H / ht;
+  g.lw = lw; g.lh = lh;
+  g.tiles_w = (W + wt - 1) / wt; g.tiles_h = (H + ht - 1) / ht;
   g.taps = op.ksize * op.ksize;
   g.kc = op.cin_pad % 64 == 0 ? 64 : 32;
   g.cin_chunks = op.cin_pad / g.kc;
@@ -102,11 +104,11 @@ void choose_brick(Op2d& op, bool rh_ok, bool p4_ok) {
   g.n_tiles = op.cout_pad / op.bn_tile;
   // resident-weight variant (conv2d_tc.cu, CfgRH): shallow 3 x 3 layers whose nine weight tiles fit in shared memory
   const bool rh_shape = (g.kc == 32 && op.bn_tile == 64 && op.cout_pad == 64) || (g.kc == 64 && op.bn_tile == 128 && op.cout_pad == 128);
-  if (rh_ok && op.ksize == 3 && g.cin_chunks == 1 && g.n_tiles == 1 && rh_shape && !op.out_f32 && W >= 16 && H >= 8) {
+  if (rh_ok && op.ksize == 3 && g.cin_chunks == 1 && g.n_tiles == 1 && rh_shape && !op.out_f32 && W % 16 == 0 && H % 8 == 0) {
     g.rh = 1;
     g.lw = 4; g.lh = 3;                       // 16 x 8 brick (also for the plain 16-bit mode)
     g.tiles_w = W / 16; g.tiles_h = H / 8;
-    if (op.pool && op.bn_tile == 64 && p4_ok && W >= 32 && H >= 16) {
+    if (op.pool && op.bn_tile == 64 && p4_ok && W % 32 == 0 && H % 16 == 0) {
       g.rh = 2;                               // pool through four accumulators: the 16 x 8 brick tiles the pooled grid
       g.tiles_w = (W / 2) / 16; g.tiles_h = (H / 2) / 8;
     }
@@ -148,7 +150,7 @@ int build_plan(a3d_enc2d* h) {
       if (cur < 0) {
         // the 3-channel image layer: CUDA-core kernel with the following pool fused (darknet.py:99-100)
         if (L.ksize != 3 || L.filters != 32 || !next_pool || (H & 1) || (W & 1)) {
-          set_error("layer %d: the image layer must be Conv2D(32, 3) followed by MaxPool2D(2,2) (Darknet19)", li);
+          set_error("layer %d: the image layer must be Conv2D(32, 3) followed by MaxPool2D(2,2) on an even size %d x %d (Darknet19)", li, H, W);
           return A3D_ERR_INVALID;
         }
         op.kind = OP_FIRST; op.pool = true;
@@ -156,7 +158,10 @@ int build_plan(a3d_enc2d* h) {
         op.kind = OP_CONV;
         op.pool = next_pool;
         op.out_f32 = next_gpool;
-        if (op.pool && ((H & 1) || (W & 1))) { set_error("layer %d: max-pool on an odd size", li); return A3D_ERR_INVALID; }
+        if (op.pool && ((H & 1) || (W & 1))) {
+          set_error("layer %d: MaxPool2D(2,2) on an odd size %d x %d (this build needs even sizes at every pool: image sizes that are multiples of 32 for Darknet19)", li, H, W);
+          return A3D_ERR_INVALID;
+        }
         op.bn_tile = op.cin_pad % 64 == 0 ? conv2d_tc_bn(op.cout_pad) : 64;   // 32-channel K steps: N tile 64 only
         choose_brick(op, !h->no_rh, !h->no_p4);
         if (op.pool && op.g.lh < 1) { set_error("layer %d: fused pool needs H >= 2", li); return A3D_ERR_INVALID; }
@@ -356,8 +361,8 @@ int a3d_enc2d_create(const a3d_enc2d_desc* d, a3d_enc2d** out) {
   *out = nullptr;
   if (d->abi_version != A3D_ABI_VERSION) { set_error("ABI version mismatch: %d vs %d", d->abi_version, A3D_ABI_VERSION); return A3D_ERR_INVALID; }
   if (d->num_layers < 1 || d->num_layers > A3D_ENC_MAX_LAYERS) { set_error("num_layers must be in [1, %d]", A3D_ENC_MAX_LAYERS); return A3D_ERR_INVALID; }
-  if (!is_pow2(d->in_h) || !is_pow2(d->in_w)) {
-    set_error("in_h / in_w must be powers of two (got %d x %d); the reference evaluates 256 x 256 crops", d->in_h, d->in_w);
+  if (d->in_h < 1 || d->in_w < 1 || d->in_h > 8192 || d->in_w > 8192) {
+    set_error("in_h / in_w must be in [1, 8192] (got %d x %d)", d->in_h, d->in_w);
     return A3D_ERR_INVALID;
   }
   if (d->operand_dtype != A3D_DTYPE_F16 && d->operand_dtype != A3D_DTYPE_BF16) { set_error("invalid operand dtype"); return A3D_ERR_INVALID; }

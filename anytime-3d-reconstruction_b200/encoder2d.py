@@ -250,7 +250,7 @@ class Encoder2D:
 
 def Darknet19(name=None, activation='elu', input_size=(256, 256), **kw) -> Encoder2D:
     """Same call as ``src.net_core.darknet.Darknet19(name, activation)`` (darknet.py:96).  The Keras model accepts
-    any image size; this build fixes it at construction (``input_size``, powers of two; the reference evaluates
+    any image size; this build fixes it at construction (``input_size``, multiples of 32; the reference evaluates
     256 x 256 crops, test_pascal_VAE_dr.py:52).  Extras: max_batch, operand_dtype, device."""
     return Encoder2D(darknet19_layers(activation), (int(input_size[0]), int(input_size[1]), 3), name=name, **kw)
 

@@ -165,7 +165,8 @@ typedef struct {
 
 typedef struct {
   int32_t abi_version;  /* A3D_ABI_VERSION */
-  int32_t in_h, in_w;   /* input height / width: powers of two (the reference runs 256 x 256, test_pascal_VAE_dr.py:52) */
+  int32_t in_h, in_w;   /* input height / width, fixed at create; every MaxPool2D must see even sizes (multiples of 32
+                           for Darknet19; the reference runs 256 x 256, test_pascal_VAE_dr.py:52) */
   int32_t in_ch;        /* 3 for images; a multiple of 64 for feature maps (head-only model) */
   int32_t num_layers;
   a3d_layer2d layers[A3D_ENC_MAX_LAYERS];

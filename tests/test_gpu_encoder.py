@@ -132,6 +132,33 @@ def test_backbone_and_head_as_separate_models_like_the_reference(a3d_mod):
     backbone.close()
 
 
+@pytest.mark.parametrize('hw', [(96, 160), (224, 224)])
+def test_image_sizes_that_are_not_powers_of_two(a3d_mod, hw):
+    """The multi-scale sizes of test_pascal_VAE_dr.py:33-60 are multiples of 32, not powers of two: power-of-two GEMM bricks
+    overhang the image, overhanging rows read zeros through TMA and are masked; rectangular images too."""
+    H, W = hw
+    layers = er.layer_list()
+    ws = er.trained_like_weights(layers, 3, seed=17, hw=64)
+    rng = np.random.Generator(np.random.PCG64(H * 1000 + W))
+    x = rng.uniform(0, 1, (3, H, W, 3)).astype(np.float32)
+    ref, ref_layers = er.forward(layers, ws, x, return_layers=True)
+    enc = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(H, W), max_batch=2)   # 3 images: 2 chunks
+    enc.set_weights(ws)
+    out = enc(x)
+    assert out.shape == (3, 32)
+    # the last chunk holds image 2
+    for li, l in enumerate(layers):
+        nxt = layers[li + 1]['kind'] if li + 1 < len(layers) else None
+        if l['kind'] in ('global_max', 'global_avg') or nxt in ('maxpool', 'global_max', 'global_avg'):
+            continue
+        got = enc.debug_layer(li, 1)
+        want = ref_layers[li].numpy()[2:3]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < ENC_REL_TOL * np.abs(want).max(), f'layer {li} {l}'
+    assert np.abs(out - ref.numpy()).max() < ENC_REL_TOL * max(np.abs(ref.numpy()).max(), 1.0)
+    enc.close()
+
+
 def test_split_sample_matches_oracle(a3d_mod, golden_enc):
     enc = a3d_mod.head2D('h', (1, 1, 64), 32, [], [], last_pooling='max', max_batch=1)
     e = golden_enc['s256_out']
@@ -191,8 +218,8 @@ def test_images_to_voxels_end_to_end(a3d_mod):
 
 
 def test_errors_like_the_reference_boundary(a3d_mod):
-    with pytest.raises(RuntimeError, match='powers of two'):
-        a3d_mod.Darknet19(input_size=(224, 224))
+    with pytest.raises(RuntimeError, match='odd size'):
+        a3d_mod.Darknet19(input_size=(200, 200))       # 200 / 8 = 25: the fourth pool would see an odd size
     enc = a3d_mod.Darknet19(input_size=(32, 32), max_batch=1)
     with pytest.raises(NotImplementedError):
         enc(np.zeros((1, 32, 32, 3), np.float32), training=True)
