@@ -229,12 +229,36 @@ def config3_aux(a3d, dev, dtype, B=128, size=256, D16=16, steps=5):
     return out
 
 
+def _stdout_to_stderr():
+    """Route fd 1 to stderr until the result line is printed: libraries (NCCL prints its version banner on stdout at
+    communicator creation) must not add lines to the one-JSON-line contract.  Returns the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _restore_stdout(saved):
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def main():
     args = parse()
+    saved_stdout = _stdout_to_stderr()
+    try:
+        _main(args, saved_stdout)
+    finally:
+        sys.stdout.flush()
+
+
+def _main(args, saved_stdout):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
+        _restore_stdout(saved_stdout)
         run_reference(args, rank, world)
         return
     import torch
@@ -379,7 +403,9 @@ def main():
             'aux_config3_images_to_voxels': aux,
             'counts_tp_fp_fn': [int(v) for v in total.tolist()], 'e2e_counts': [int(v) for v in e2e_counts.tolist()],
         }
+        _restore_stdout(saved_stdout)
         print(json.dumps(line), flush=True)
+        saved_stdout = _stdout_to_stderr()   # anything printed during teardown stays off stdout
     if dist is not None:
         dist.destroy_process_group()
 
