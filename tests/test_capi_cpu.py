@@ -81,3 +81,66 @@ def test_iou_from_counts():
     import a3d
     m, g = a3d.iou_from_counts(np.array([[5, 10, 5], [0, 0, 0]]))
     assert g == pytest.approx(0.25) and m == pytest.approx((0.25 + 1.0) / 2)
+
+
+def test_encoder_handles_validate_structure_before_touching_a_device():
+    """a3d_enc2d_create / a3d_enc3d_create reject unsupported structures with A3D_ERR_INVALID (-1) and a message, and
+    report A3D_ERR_NO_DEVICE (-3) for a valid structure when no GPU is present (no CPU fallback)."""
+    from a3d import _capi
+    from a3d.encoder2d import darknet19_layers, head2d_layers
+    lib = _capi.lib()
+
+    def enc2d_desc(layers, h, w, c):
+        d = _capi.Enc2dDesc()
+        d.abi_version, d.in_h, d.in_w, d.in_ch, d.num_layers = 1, h, w, c, len(layers)
+        for i, l in enumerate(layers):
+            d.layers[i].kind = _capi.L2D[l['kind']]
+            if l['kind'] == 'conv':
+                d.layers[i].filters, d.layers[i].ksize = l['filters'], l['ksize']
+                d.layers[i].batch_norm, d.layers[i].activation = int(l['bn']), _capi.ACT2D[l['act']]
+        d.max_batch, d.operand_dtype = 4, 0
+        return d
+
+    h = C.c_void_p()
+    full = darknet19_layers() + head2d_layers(32, [], [], 'max')
+    assert C.sizeof(_capi.Enc2dDesc) == 4 * (5 + 5 * 40 + 3)
+    rc = lib.a3d_enc2d_create(C.byref(enc2d_desc(full, 256, 256, 3)), C.byref(h))
+    assert rc == (0 if torch.cuda.is_available() else -3)
+    if rc == 0:
+        lib.a3d_enc2d_destroy(h)
+    assert lib.a3d_enc2d_create(C.byref(enc2d_desc(full, 200, 200, 3)), C.byref(h)) == -1        # 25 x 25 at the 4th pool
+    assert b'odd size' in lib.a3d_last_error()
+    assert lib.a3d_enc2d_create(C.byref(enc2d_desc(full, 256, 256, 5)), C.byref(h)) == -1
+    assert b'in_ch must be 3' in lib.a3d_last_error()
+    bad = [dict(full[0], ksize=5)] + full[1:]
+    assert lib.a3d_enc2d_create(C.byref(enc2d_desc(bad, 256, 256, 3)), C.byref(h)) == -1
+    assert lib.a3d_enc2d_create(C.byref(enc2d_desc([{'kind': 'global_max'}], 8, 8, 64)), C.byref(h)) == -1
+    assert b'global pool' in lib.a3d_last_error()
+
+    d3 = _capi.Enc3dDesc()
+    d3.abi_version, d3.in_grid, d3.num_layers, d3.final_pool, d3.activation, d3.max_batch = 1, 64, 5, 1, 1, 4
+    for i, (f, s) in enumerate(zip([64, 128, 256, 512, 128], [2, 2, 2, 2, 1])):
+        d3.filters[i], d3.ksizes[i], d3.strides[i] = f, 4, s
+    assert C.sizeof(_capi.Enc3dDesc) == 4 * (3 + 3 * 8 + 6)
+    rc = lib.a3d_enc3d_create(C.byref(d3), C.byref(h))
+    assert rc == (0 if torch.cuda.is_available() else -3)
+    if rc == 0:
+        lib.a3d_enc3d_destroy(h)
+    d3.strides[3] = 1
+    assert lib.a3d_enc3d_create(C.byref(d3), C.byref(h)) == -1
+    assert b'unsupported encoder3D structure' in lib.a3d_last_error()
+    d3.strides[3] = 2
+    d3.filters[2] = 200
+    assert lib.a3d_enc3d_create(C.byref(d3), C.byref(h)) == -1
+
+
+def test_python_mirrors_of_the_encoders_refuse_to_run_without_a_gpu():
+    import a3d
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError, match='no CPU'):
+        a3d.Darknet19()
+    with pytest.raises(RuntimeError, match='no CPU'):
+        a3d.encoder3D(a3d.presets.MODELNET_ENCODER)
+    with pytest.raises(KeyError):
+        a3d.encoder3D({'name': 'x'})
