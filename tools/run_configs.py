@@ -19,7 +19,7 @@ import torch
 
 import a3d
 from a3d.presets import MODELNET_DECODER, PASCAL_DECODER
-from oracle import anytime_ref as ar, decoder_ref as dr
+from oracle import anytime_ref as ar, decoder_ref as dr, encoder2d_ref as er, encoder3d_ref as e3
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--configs', default='1,2,3,4,5')
@@ -125,8 +125,7 @@ if 2 in todo and rank == 0:
     dec.close()
 
 if 3 in todo and rank == 0:
-    # config 3: Pascal3D decoder path, D = 16, C = 12, B = 128; the image encoder is out of scope, so the
-    # latents come from synthetic (mean, logvar) through sampling()
+    # config 3, decoder half only: latents from synthetic (mean, logvar) through sampling() (the end-to-end run follows)
     ws_p = dr.trained_like_weights(PASCAL_DECODER, 1236)
     dec = a3d.decoder3D(PASCAL_DECODER, max_chunk=128, device=local)
     dec.set_weights(ws_p)
@@ -139,7 +138,73 @@ if 3 in todo and rank == 0:
     zc = z[:, None, :].contiguous()
     out, ms = timed(lambda: a3d.anytime_eval(dec, None, None, None, bits, z_completed=zc))
     par = parity(dec, PASCAL_DECODER, ws_p, zc.cpu().numpy(), tgt, out['counts'])
-    emit(3, 'Pascal3D decoder from synthetic (mean, logvar) B=128 K=1', B, 1, ms, par)
+    emit(3, 'Pascal3D decoder only, from synthetic (mean, logvar) B=128 K=1', B, 1, ms, par)
+    dec.close()
+
+if 3 in todo and rank == 0:
+    # config 3 end to end (SURVEY 8f-1 built): synthetic RGB crops [128,256,256,3] U[0,1] -> Darknet19 + head2D -> mean /
+    # clipped logvar -> sampling -> decoder -> counts.  FLOP = encoder (algorithmic) + decoder per object.
+    B, size = 128, 256
+    layers = er.layer_list()
+    ews = er.trained_like_weights(layers, 3, seed=1240, hw=size)
+    ws_p = dr.trained_like_weights(PASCAL_DECODER, 1236)
+    enc = a3d.image_encoder(a3d.presets.PASCAL_ENCODER_HEAD, input_size=(size, size), max_batch=B, device=local)
+    enc.set_weights(ews)
+    dec = a3d.decoder3D(PASCAL_DECODER, max_chunk=128, device=local)
+    dec.set_weights(ws_p)
+    x = rng.uniform(0, 1, (B, size, size, 3)).astype(np.float32)
+    xd = torch.from_numpy(x).to(dev)
+    tgt = ar.make_targets(rng, B)
+    bits = torch.from_numpy(ar.pack_bits(tgt)).to(dev)
+
+    def run3():
+        _, _, z = enc.encode(xd, 16, seed=21)
+        return a3d.anytime_eval(dec, None, None, None, bits, z_completed=z[:, None, :].contiguous(), return_grid=False), z
+    (out, z), ms = timed(run3)
+    n = args.oracle_objects
+    _, _, rz = er.split_sample(er.forward(layers, ews, x[:n]).numpy(), 16, seed=21)
+    ref_mp, ref_cnt = ar.anytime_eval(PASCAL_DECODER, ws_p, rz[:, None, :], tgt[:n])
+    r = a3d.anytime_eval(dec, None, None, None, tgt[:n], z_completed=z[:n, None, :].contiguous(), return_grid=True)
+    mp, cnt = r['mean_prob'].cpu().numpy(), r['counts'].cpu().numpy()
+    par = {'max_abs_dp': float(np.abs(mp - ref_mp).max()), 'flipped_pct': float(100 * ((mp >= .5) != (ref_mp >= .5)).mean()),
+           'd_iou_global': abs(ar.iou_from_counts(cnt)[1] - ar.iou_from_counts(ref_cnt)[1]), 'oracle_objects': n,
+           'max_abs_dz': float(np.abs(z[:n].cpu().numpy() - rz).max())}
+    alg, _ = er.encoder_macs(layers, size, size, 3)
+    keep = FLOP
+    FLOP = 2.0 * alg + 6.663781376e9
+    emit(3, 'Pascal3D images -> Darknet19+head2D -> decoder -> counts B=128 K=1 (end to end)', B, 1, ms, par)
+    FLOP = keep
+    enc.close()
+    dec.close()
+
+if 1 in todo and rank == 0:
+    # config 1 with its encoder (test_modelnet_VAE path): voxels -> encoder3D -> sampling -> decoder -> counts, B = 32
+    B = 32
+    ews = e3.trained_like_weights(e3.MODELNET_ENCODER, 1241)
+    enc = a3d.encoder3D(a3d.presets.MODELNET_ENCODER, max_batch=B, device=local)
+    enc.set_weights(ews)
+    dec = a3d.decoder3D(MODELNET_DECODER, max_chunk=32, device=local)
+    dec.set_weights(ws_tr)
+    vox = ar.make_targets(rng, B)
+    vd = torch.from_numpy(vox).to(dev)
+    bits = torch.from_numpy(ar.pack_bits(vox)).to(dev)
+
+    def run1():
+        _, _, z = enc.encode(vd, 64, seed=22)
+        return a3d.anytime_eval(dec, None, None, None, bits, z_completed=z[:, None, :].contiguous()), z
+    (out, z), ms = timed(run1)
+    n = args.oracle_objects
+    _, _, rz = er.split_sample(e3.forward(e3.MODELNET_ENCODER, ews, vox[:n]).numpy(), 64, seed=22)
+    ref_mp, ref_cnt = ar.anytime_eval(MODELNET_DECODER, ws_tr, rz[:, None, :], vox[:n])
+    r = a3d.anytime_eval(dec, None, None, None, vox[:n], z_completed=z[:n, None, :].contiguous(), return_grid=True)
+    mp, cnt = r['mean_prob'].cpu().numpy(), r['counts'].cpu().numpy()
+    par = {'max_abs_dp': float(np.abs(mp - ref_mp).max()), 'flipped_pct': float(100 * ((mp >= .5) != (ref_mp >= .5)).mean()),
+           'd_iou_global': abs(ar.iou_from_counts(cnt)[1] - ar.iou_from_counts(ref_cnt)[1]), 'oracle_objects': n}
+    keep = FLOP
+    FLOP = 2.0 * e3.encoder_macs(e3.MODELNET_ENCODER)[0] + 6.663830528e9
+    emit(1, 'ModelNet voxels -> encoder3D -> decoder -> counts B=32 K=1 (end to end)', B, 1, ms, par)
+    FLOP = keep
+    enc.close()
     dec.close()
 
 if 4 in todo:
