@@ -13,6 +13,8 @@ collective is one all-reduce of the integer counts).
 `e2e`    : same metric through the host-buffer C-ABI call a3d_anytime_eval_host (numpy in, counts out; H2D + D2H
            inside the timed region).
 `roofline`: the dominant kernel (128->64 transposed-conv implicit GEMM) against the measured bf16 tensor peak.
+`oracle/` is used here in two ways only: as the timed CPU baseline (below), and as the seeded numpy generator of the
+           synthetic inputs / random-init weights (no device compute goes through it).
 `cpu_baseline` / `--impl reference`: the torch-CPU-fp32 oracle (the reference itself needs TensorFlow, which is not
            installable offline -- see DESIGN.md) on a bounded sample, on the host cores.
 """

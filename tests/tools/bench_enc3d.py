@@ -1,6 +1,6 @@
 """Throughput of the CUDA voxel encoder (encoder3D) on synthetic occupancy grids: objects/s and TFLOP/s.
 
-    python tools/bench_enc3d.py [--batch 256] [--steps 10]
+    python tests/tools/bench_enc3d.py [--batch 256] [--steps 10]
 """
 import argparse
 import os
@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import a3d  # noqa: E402

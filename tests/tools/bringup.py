@@ -1,7 +1,7 @@
 """GPU bring-up diagnostic: per-layer comparison of the CUDA path with the torch-fp32 oracle.
-Usage: python tools/bringup.py [simt|tcgen05] [fp16|bf16] [n]"""
+Usage: python tests/tools/bringup.py [simt|tcgen05] [fp16|bf16] [n]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import a3d
 from a3d.presets import MODELNET_DECODER

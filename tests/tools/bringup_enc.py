@@ -1,6 +1,6 @@
 """Bring-up / diagnostic: per-layer comparison of the CUDA image encoder against the torch-CPU oracle.
 
-    python tools/bringup_enc.py [--size 64] [--n 3] [--dtype fp16] [--init trained|keras]
+    python tests/tools/bringup_enc.py [--size 64] [--n 3] [--dtype fp16] [--init trained|keras]
 """
 import argparse
 import os
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import a3d  # noqa: E402

@@ -1,7 +1,7 @@
 """GPU diagnostic: anytime_eval (K-mean + counts) vs the oracle on the GPU-completed latents.
-Usage: python tools/check_eval.py [tcgen05|simt] [B] [K]"""
+Usage: python tests/tools/check_eval.py [tcgen05|simt] [B] [K]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import a3d
 from a3d.presets import MODELNET_DECODER

@@ -2,7 +2,7 @@
 (BASELINE.md section 4).  Single process = one GPU; under torchrun the objects of configs 4 and 5 are sharded over the
 ranks and the counts are all-reduced (NCCL).
 
-    python tools/run_configs.py [--configs 1,2,3,4,5] [--scale 1.0]
+    python tests/tools/run_configs.py [--configs 1,2,3,4,5] [--scale 1.0]
 
 Parity columns (max |dp|, flipped voxels, dIoU) compare against the CPU oracle on a small subsample of each config
 (the oracle decodes ~20 latents/s); throughput columns are CUDA-event timed over the full config.
@@ -13,7 +13,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

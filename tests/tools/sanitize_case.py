@@ -1,6 +1,6 @@
 """Tiny end-to-end case for compute-sanitizer (decode + anytime_eval, both L4 kernels)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import a3d
 from a3d.presets import MODELNET_DECODER

@@ -1,6 +1,6 @@
-"""Per-stage device times of one anytime_eval chunk (diagnostic).  Usage: python tools/stage_times.py [n_obj] [K] [reps]"""
+"""Per-stage device times of one anytime_eval chunk (diagnostic).  Usage: python tests/tools/stage_times.py [n_obj] [K] [reps]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import a3d
 from a3d.presets import MODELNET_DECODER
