@@ -13,6 +13,8 @@
 // gathers the 4 x 4 x 4 neighbourhood of output voxel r from the fp32 grid, rounds it to the operand type and stores
 // row r of the A tile itself (SWIZZLE_128B: 16-byte chunk c of row r at chunk c ^ (r & 7)); four tcgen05.mma
 // (M = 128, N = 64, K = 16) against the resident 64 x 64 weight tile.
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
@@ -24,25 +26,30 @@ constexpr int BM = 128;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 
-template <int BN>
+// MT = M tiles per unit.  MT = 2 (128-wide N tiles only): two 128-voxel bricks share every weight tile of a K step (two
+// MMAs per K substep against the same B descriptor, two accumulators of BN columns) -- the 64 -> 128 layer streams its
+// whole 1 MB weight set per brick otherwise and is bound by L2 -> SM operand traffic, not by the tensor pipe.
+template <int BN, int MT>
 struct Cfg3 {
-  static constexpr int A_BYTES = BM * 128;
+  static constexpr int A_BYTES = MT * BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? 4 : (MT == 2 ? 4 : 6);
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int STAGING_BYTES = kEpiWarps * 32 * 64;   // 2 KB per epilogue warp: 32 rows x 32 columns x 16 bit
   static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + NUM_BARS * 8 + 16;
 };
 
 // MODE 0: 16-bit [voxels, cout_pad]; 1: fp32 [voxels, cout_real] (final conv, feeds the global pool)
-template <int BN, int FMT, int ACT, int MODE>
+template <int BN, int FMT, int ACT, int MODE, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
                  void* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
                  Conv3dGeom g) {
-  using C = Cfg3<BN>;
-  constexpr int CW = BN / 4;   // columns per epilogue warp (4 warps per TMEM lane quarter)
+  using C = Cfg3<BN, MT>;
+  static_assert(MT == 1 || (MT == 2 && BN == 128), "two M tiles per unit are built for 128-wide N tiles");
+  constexpr int CW = MT * BN / 4;   // columns per epilogue warp: 4 warps per TMEM lane quarter, split over (M tile, columns)
   constexpr int A_BYTES = C::A_BYTES;
+  constexpr int TBUF = MT * BN;     // TMEM columns per accumulator buffer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -57,7 +64,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_units = g.m_tiles * g.n_tiles;
+  const int total_units = (g.m_tiles / MT) * g.n_tiles;   // the host launches MT = 2 only for an even tile count
   const int ksteps = 64 * g.cin_chunks;
   const int tiles_per_obj = g.tiles_w * g.tiles_h * g.tiles_d;
 
@@ -87,11 +94,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     uint32_t ph = 0, cnt = 0;
     static_assert(C::STAGES % 2 == 0, "two producer warps need an even stage count");
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int nt = u % g.n_tiles, mt = u / g.n_tiles;
-      const int tb = mt % tiles_per_obj, nb = mt / tiles_per_obj;
-      const int tw = tb % g.tiles_w, th = (tb / g.tiles_w) % g.tiles_h, td = tb / (g.tiles_w * g.tiles_h);
-      const int w0 = ((tw << g.lw) * g.stride) - 1, h0 = ((th << g.lh) * g.stride) - 1, d0 = ((td << g.ld) * g.stride) - 1;
-      const int n0 = nb << (7 - g.lw - g.lh - g.ld);
+      const int nt = u % g.n_tiles, mu = u / g.n_tiles;
+      int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const int mt = mu * MT + t;
+        const int tb = mt % tiles_per_obj, nb = mt / tiles_per_obj;
+        const int tw = tb % g.tiles_w, th = (tb / g.tiles_w) % g.tiles_h, td = tb / (g.tiles_w * g.tiles_h);
+        w0[t] = ((tw << g.lw) * g.stride) - 1; h0[t] = ((th << g.lh) * g.stride) - 1; d0[t] = ((td << g.ld) * g.stride) - 1;
+        n0[t] = nb << (7 - g.lw - g.lh - g.ld);
+      }
       int brow = nt * BN;
       for (int kd = 0; kd < 4; ++kd)
         for (int kh = 0; kh < 4; ++kh)
@@ -101,7 +113,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
               ptx::mbar_wait(&empty[s], ph ^ 1);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(&full[s], A_BYTES + C::B_BYTES);
-                ptx::tma_load_5d(smem_a + s * A_BYTES, &tmap_act, &full[s], kc * 64, w0 + kw, h0 + kh, d0 + kd, n0);
+#pragma unroll
+                for (int t = 0; t < MT; ++t)
+                  ptx::tma_load_5d(smem_a + s * A_BYTES + t * (BM * 128), &tmap_act, &full[s], kc * 64, w0[t] + kw, h0[t] + kh,
+                                   d0[t] + kd, n0[t]);
                 ptx::tma_load_2d(smem_b + s * C::B_BYTES, &tmap_wgt, &full[s], kc * 64, brow);
               }
               __syncwarp();
@@ -122,7 +137,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_empty[buf], ((unit_it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + buf * BN;
+      const uint32_t tacc = tmem_base + buf * TBUF;
       for (int ks = 0; ks < ksteps; ++ks) {
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
@@ -130,7 +145,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         if (ptx::elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            ptx::umma_f16<1>(tacc, ptx::sw128_desc(a_lo + kk * 2), ptx::sw128_desc(b_lo + kk * 2), idesc, (ks | kk) != 0);
+#pragma unroll
+            for (int t = 0; t < MT; ++t)
+              ptx::umma_f16<1>(tacc + t * BN, ptx::sw128_desc(a_lo + t * ((BM * 128) >> 4) + kk * 2), ptx::sw128_desc(b_lo + kk * 2),
+                               idesc, (ks | kk) != 0);
           ptx::umma_commit<1>(&empty[s]);
           if (ks == ksteps - 1) ptx::umma_commit<1>(&t_full[buf]);
         }
@@ -141,16 +159,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   } else if (warp >= 4) {
     // ===================================================== epilogue: TMEM -> BN -> act -> global
     const int e = warp - 4;
-    const int quarter = e & 3, cgrp = e >> 2;
+    const int quarter = e & 3;
+    const int half = MT == 2 ? (e >> 2) & 1 : 0;      // which M tile of the unit
+    const int cgrp = MT == 2 ? e >> 3 : e >> 2;       // column group of CW columns
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     constexpr int GROUPS = CW / 32;
     uint32_t unit_it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++unit_it) {
-      const int nt = u % g.n_tiles, mt = u / g.n_tiles;
+      const int nt = u % g.n_tiles, mt = (u / g.n_tiles) * MT + half;
       const int buf = unit_it & 1;
       ptx::mbar_wait(&t_full[buf], (unit_it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + lane_base + buf * BN + cgrp * CW;
+      const uint32_t tacc = tmem_base + lane_base + buf * TBUF + half * BN + cgrp * CW;
       const int tb = mt % tiles_per_obj, nb = mt / tiles_per_obj;
       const int tw = tb % g.tiles_w, th = (tb / g.tiles_w) % g.tiles_h, td = tb / (g.tiles_w * g.tiles_h);
       const int r = quarter * 32 + lane;
@@ -353,20 +373,20 @@ conv3d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
   if (warp == 0) ptx::tmem_dealloc<1>(tmem, 64);
 }
 
-template <int BN, int FMT, int MODE>
+template <int BN, int FMT, int MODE, int MT>
 int launch_act(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const float* scale, const float* shift,
                const Conv3dGeom& g, int act, int grid, cudaStream_t st) {
   auto launch = [&](auto kern) -> int {
-    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<BN>::SMEM_BYTES));
-    kern<<<grid, kThreads, Cfg3<BN>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
+    A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<BN, MT>::SMEM_BYTES));
+    kern<<<grid, kThreads, Cfg3<BN, MT>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };
   switch (act) {
-    case A3D_ACT_ELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_ELU, MODE>);
-    case A3D_ACT_RELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_RELU, MODE>);
-    case A3D_ACT_LRELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_LRELU, MODE>);
-    case A3D_ACT_NONE: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_NONE, MODE>);
+    case A3D_ACT_ELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_ELU, MODE, MT>);
+    case A3D_ACT_RELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_RELU, MODE, MT>);
+    case A3D_ACT_LRELU: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_LRELU, MODE, MT>);
+    case A3D_ACT_NONE: return launch(conv3d_tc_kernel<BN, FMT, A3D_ACT_NONE, MODE, MT>);
     default: set_error("conv3d: unsupported activation %d", act); return A3D_ERR_INVALID;
   }
 }
@@ -377,17 +397,21 @@ int launch_conv3d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, v
                      const float* shift, const Conv3dGeom& g, int bn, int fmt, int act, bool out_f32, int num_sms,
                      cudaStream_t st, int64_t* launches) {
   if (g.n_objects <= 0) return A3D_OK;
-  const int total = g.m_tiles * g.n_tiles;
+  // two bricks per unit share the weight tiles when the N tile is 128 wide and the brick count is even
+  static const bool no_mt2 = [] { const char* e = getenv("A3D_ENC3D_MT2"); return e && e[0] == '0'; }();
+  const bool mt2 = bn == 128 && (g.m_tiles % 2) == 0 && !no_mt2 && (g.m_tiles / 2) * g.n_tiles >= num_sms;   // keep every SM busy
+  const int total = (g.m_tiles / (mt2 ? 2 : 1)) * g.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   int rc;
-#define A3D_C3D(BN_)                                                                                              \
-  (fmt == A3D_DTYPE_F16                                                                                            \
-       ? (out_f32 ? launch_act<BN_, A3D_DTYPE_F16, 1>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)      \
-                  : launch_act<BN_, A3D_DTYPE_F16, 0>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st))     \
-       : (out_f32 ? launch_act<BN_, A3D_DTYPE_BF16, 1>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)     \
-                  : launch_act<BN_, A3D_DTYPE_BF16, 0>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)))
-  if (bn == 256) rc = A3D_C3D(256);
-  else if (bn == 128) rc = A3D_C3D(128);
+#define A3D_C3D(BN_, MT_)                                                                                               \
+  (fmt == A3D_DTYPE_F16                                                                                                  \
+       ? (out_f32 ? launch_act<BN_, A3D_DTYPE_F16, 1, MT_>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)       \
+                  : launch_act<BN_, A3D_DTYPE_F16, 0, MT_>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st))      \
+       : (out_f32 ? launch_act<BN_, A3D_DTYPE_BF16, 1, MT_>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)      \
+                  : launch_act<BN_, A3D_DTYPE_BF16, 0, MT_>(tmap_act, tmap_wgt, out, scale, shift, g, act, grid, st)))
+  if (bn == 256) rc = A3D_C3D(256, 1);
+  else if (bn == 128 && mt2) rc = A3D_C3D(128, 2);
+  else if (bn == 128) rc = A3D_C3D(128, 1);
   else { set_error("conv3d: N tile must be 128 or 256"); return A3D_ERR_INVALID; }
 #undef A3D_C3D
   if (rc == A3D_OK && launches) ++*launches;
