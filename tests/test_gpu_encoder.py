@@ -261,3 +261,18 @@ def test_tf_checkpoint_weight_io_round_trip(a3d_mod, tmp_path):
     x = _images(32, 2, 6)
     assert np.array_equal(enc(x), enc2(x))
     enc.close(); enc2.close()
+
+
+def test_empty_batch_and_smallest_image(a3d_mod):
+    """n = 0 returns an empty result; a 32 x 32 image ends in a 1 x 1 feature map (bricks of 128 images)."""
+    layers = er.layer_list()
+    ws = er.trained_like_weights(layers, 3, seed=23, hw=32)
+    enc = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(32, 32), max_batch=5)
+    enc.set_weights(ws)
+    assert enc(np.zeros((0, 32, 32, 3), np.float32)).shape == (0, 32)
+    x = _images(32, 7, 12)                                             # 7 images, max_batch 5: two ragged chunks
+    out = enc(x)
+    ref = er.forward(layers, ws, x).numpy()
+    assert out.shape == (7, 32)
+    assert np.abs(out - ref).max() < ENC_REL_TOL * max(np.abs(ref).max(), 1.0)
+    enc.close()

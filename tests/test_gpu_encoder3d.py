@@ -117,3 +117,19 @@ def test_errors_and_weight_io(a3d_mod, tmp_path):
     x = ar.make_targets(np.random.default_rng(0), 2)
     assert np.array_equal(enc(x), enc2(x))
     enc.close(); enc2.close()
+
+
+def test_empty_and_single_object_batches(a3d_mod):
+    st = e3.MODELNET_ENCODER
+    ws = e3.keras_default_weights(st, 4)
+    enc = a3d_mod.encoder3D(st, max_batch=3)
+    enc.set_weights(ws)
+    out0 = enc(np.zeros((0, 64, 64, 64, 1), np.float32))
+    assert out0.shape == (0, 128)
+    x = ar.make_targets(np.random.default_rng(11), 1)
+    out1 = enc(x)
+    ref = e3.forward(st, ws, x).numpy()
+    assert out1.shape == (1, 128) and np.abs(out1 - ref).max() < 1e-2 * max(np.abs(ref).max(), 1e-3)
+    z = np.zeros((1, 64, 64, 64, 1), np.float32)                     # an empty grid: every layer sees only its BN shift
+    assert np.abs(enc(z) - e3.forward(st, ws, z).numpy()).max() < 1e-3
+    enc.close()
