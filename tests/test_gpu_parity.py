@@ -381,3 +381,37 @@ def test_ragged_decode_sizes_match_simt_path(a3d_mod, weights, n):
     s.set_weights(ws)
     a, b = t(z), s(z)
     assert np.isfinite(a).all() and np.abs(a - b).max() < 5e-3 and flips(a, b) < 2e-4
+
+
+def test_getEval_values_match_the_oracle_composition(a3d_mod, decoders, weights):
+    """nolbo.py:1472-1528 recomposed from oracle pieces (mean fill -> decode -> binary_loss(0.6) / precision / recall /
+    nearest-prior accuracy; prior-sample fill with the same Philox draws -> K-mean decode -> the same metrics) against
+    the 10-tuple a3d.getEval returns for an explicit mask."""
+    dec, ws = decoders[('mn', 'trained')], weights[('mn', 'trained')]
+    rng = np.random.default_rng(31)
+    B, D, K = 4, 64, 2
+    z = dr.round_bf16(rng.standard_normal((B, D)).astype(np.float32))
+    mu = rng.standard_normal((40, D)).astype(np.float32)
+    mask = ar.bernoulli_mask(rng, B, D, 0.5)
+    tgt = ar.make_targets(rng, B)
+    cat = np.eye(40, dtype=np.float32)[rng.integers(0, 40, B)]
+    out = a3d_mod.getEval(dec, (z, tgt, cat), mu, missing_prob=0.5, K=K, seed=9, mask=mask)
+
+    def metrics(prob, cnt, zc):
+        c = cnt.astype(np.float64)
+        pr = float((c[:, 0] / (c[:, 0] + c[:, 1] + 1e-10)).mean())                      # nolbo.py:1499-1501
+        rc = float((c[:, 0] / (c[:, 0] + c[:, 2] + 1e-10)).mean())
+        loss = float(ar.binary_loss(prob, tgt, gamma=0.6).mean())                        # :1497-1498
+        acc = float((((zc[:, None, :] - mu[None]) ** 2).sum(-1).argmin(-1) == cat.argmax(-1)).mean())   # :1488-1494
+        return loss, pr, rc, acc
+
+    z_mean, _ = ar.impute(z, mask, mu, 1, seed=9, fill='mean')                           # :1477-1482
+    p0, c0 = ar.anytime_eval(dr.MODELNET_DECODER, ws, z_mean, tgt)
+    zc, _ = ar.impute(z, mask, mu, K, seed=9, fill='prior_sample')                       # :1505-1510 (K draws)
+    p1, c1 = ar.anytime_eval(dr.MODELNET_DECODER, ws, zc, tgt)
+    for got_prob, got, (prob, cnt, zz) in ((out[0], out[1:5], (p0, c0, z_mean[:, 0])), (out[5], out[6:10], (p1, c1, zc[:, 0]))):
+        loss, pr, rc, acc = metrics(prob, cnt, zz)
+        assert np.abs(got_prob.cpu().numpy() - prob).max() < PROB_TOL
+        assert got[0] == pytest.approx(loss, rel=2e-3)
+        assert got[1] == pytest.approx(pr, abs=2e-3) and got[2] == pytest.approx(rc, abs=2e-3)
+        assert got[3] == pytest.approx(acc, abs=1e-9)
