@@ -31,7 +31,7 @@ struct Op2d {
   int w_index = -1;           // index of the kernel variable in the Keras weight list
   int bn_tile = 0;
   Conv2dGeom g;
-  CUtensorMap tmap_act, tmap_wgt;
+  CUtensorMap tmap_act, tmap_wgt, tmap_wgt_half;   // _half: (64, 128)-row box for the 2-CTA kernel (256-wide N tiles)
   void* wgt = nullptr;        // device: 16-bit [tap][cout_pad][cin_pad]; first layer: fp32 [27][32] (CUDA-core kernel)
   void* wgt_first16 = nullptr; // first layer, tensor-core kernel: 16-bit [32 co][32 k], k = tap*3 + ci, 5 zero columns
   float *scale = nullptr, *shift = nullptr;
@@ -261,6 +261,12 @@ int make_maps(a3d_enc2d* h, Op2d& op) {
   r = enc(&op.tmap_wgt, dt, 2, op.wgt, wd, ws, wb, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder weights, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
+  if (op.bn_tile == 256 && kc == 64) {
+    cuuint32_t wh[2] = {64, 128};
+    r = enc(&op.tmap_wgt_half, dt, 2, op.wgt, wd, ws, wh, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(encoder half weights, layer %d) failed: %d", op.layer, (int)r); return A3D_ERR_CUDA; }
+  }
   return A3D_OK;
 }
 
@@ -328,8 +334,12 @@ int run_chunk(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* o
         const int nt = 128 >> (g.lw + g.lh);
         g.n_images = (int)n;
         g.m_tiles = (int)((n + nt - 1) / nt) * g.tiles_w * g.tiles_h;
-        rc = launch_conv2d_tc(op.tmap_act, op.tmap_wgt, out, op.scale, op.shift, g, op.bn_tile, fmt, op.act, op.pool,
-                              op.out_f32, h->num_sms, st, &h->launches);
+        if (conv2d_pair_eligible(g, op.bn_tile, op.pool, op.out_f32))
+          rc = launch_conv2d_pair(op.tmap_act, op.tmap_wgt_half, out, op.scale, op.shift, g, fmt, op.act, op.pool,
+                                  h->num_sms, st, &h->launches);
+        else
+          rc = launch_conv2d_tc(op.tmap_act, op.tmap_wgt, out, op.scale, op.shift, g, op.bn_tile, fmt, op.act, op.pool,
+                                op.out_f32, h->num_sms, st, &h->launches);
         break;
       }
       case OP_POOL:

@@ -107,6 +107,12 @@ int conv2d_tc_bn(int cout_pad);
 int launch_conv2d_tc(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
                      const float* shift, const Conv2dGeom& g, int bn, int fmt, int act, bool pool, bool out_f32,
                      int num_sms, cudaStream_t st, int64_t* launches);
+// 2-CTA (cta_group::2) variant for 256-wide N tiles (conv2d_pair.cu): two bricks per cluster share every weight tile.
+// tmap_wgt_half = the weight tensor with a (64, 128)-row box.
+bool conv2d_pair_eligible(const Conv2dGeom& g, int bn, bool pool, bool out_f32);
+int launch_conv2d_pair(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt_half, void* out, const float* scale,
+                       const float* shift, const Conv2dGeom& g, int fmt, int act, bool pool, int num_sms, cudaStream_t st,
+                       int64_t* launches);
 // first layer: Conv2D(3 -> 32, k3) + BN + act + MaxPool2D(2,2); in fp32 [n,H,W,3], out 16-bit [n,H/2,W/2,cout_pad]
 int launch_conv2d_first_pool(const float* in, const float* w27x32, const float* scale, const float* shift, void* out,
                              int64_t n, int H, int W, int cout_pad, int fmt, int act, cudaStream_t st, int64_t* launches);
