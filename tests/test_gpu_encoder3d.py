@@ -133,3 +133,22 @@ def test_empty_and_single_object_batches(a3d_mod):
     z = np.zeros((1, 64, 64, 64, 1), np.float32)                     # an empty grid: every layer sees only its BN shift
     assert np.abs(enc(z) - e3.forward(st, ws, z).numpy()).max() < 1e-3
     enc.close()
+
+
+def test_encoder3d_matches_golden_fixture(a3d_mod):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with np.load(os.path.join(root, 'tests', 'golden', 'golden_enc3d_v1.npz')) as f:
+        g = {k: f[k] for k in f.files}
+    st = e3.MODELNET_ENCODER
+    enc = a3d_mod.encoder3D(st, max_batch=4)
+    enc.set_weights(e3.trained_like_weights(st, 401))
+    x = ar.make_targets(np.random.Generator(np.random.PCG64(402)), 3)
+    out = enc(x)
+    assert np.abs(out - g['out']).max() < OUT_TOL
+    for li in range(4):
+        got = enc.debug_layer(li, 3).reshape(3, -1)
+        step = max(1, got.shape[1] // 64)
+        want = g['layer_samples'][li]
+        assert np.abs(got[:, ::step][:, :64] - want).max() < REL_TOL * max(np.abs(want).max(), 1.0)
+    enc.close()

@@ -39,3 +39,18 @@ def test_forward_shapes_pool_and_final_activation():
     # first layer against the definition, through BN (identity statistics at init) and ELU
     pre = e3.conv3d_same_definition(x.astype(np.float64), ws[0].astype(np.float64), 2) / np.sqrt(1 + 1e-3)
     np.testing.assert_allclose(outs[0].numpy(), np.where(pre > 0, pre, np.expm1(pre)), atol=1e-10)
+
+
+def test_oracle_reproduces_committed_fixture():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with np.load(os.path.join(root, 'tests', 'golden', 'golden_enc3d_v1.npz')) as f:
+        g = {k: f[k] for k in f.files}
+    st = e3.MODELNET_ENCODER
+    ws = e3.trained_like_weights(st, 401)
+    np.testing.assert_allclose([np.asarray(w, np.float64).sum() for w in ws], g['wsum'], rtol=1e-9, atol=1e-9)
+    x = ar.make_targets(np.random.Generator(np.random.PCG64(402)), 3)
+    assert np.array_equal(x.reshape(3, -1).sum(1).astype(np.int64), g['x_occupancy'])
+    y, outs = e3.forward(st, ws, x, return_layers=True)
+    np.testing.assert_allclose(y.numpy(), g['out'], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose([float(o.double().abs().sum()) for o in outs], g['layer_abs'], rtol=1e-4)
