@@ -378,7 +378,7 @@ def _main(args, saved_stdout):
                                'algorithmic_bytes_per_launch': tail_bytes}}
 
     aux = None
-    if rank == 0:
+    if rank == 0 and world == 1:   # secondary measurement and CPU baseline: single-process runs only
         try:
             aux = config3_aux(a3d, dev, args.dtype)
         except Exception as e:   # the secondary measurement must never take the headline line down
@@ -386,7 +386,7 @@ def _main(args, saved_stdout):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             rate, secs = cpu_reference_rate(40)     # ~10 s of CPU work on the 16-thread host (bounded sample)
             cpu = {'value': rate, 'unit': 'objects/s', 'cores': os.cpu_count(), 'kind': 'port',
                    'sample': f'40 objects x K={K} = 640 decodes of the same workload in {secs:.1f} s, torch CPU fp32 '
