@@ -144,3 +144,22 @@ def test_python_mirrors_of_the_encoders_refuse_to_run_without_a_gpu():
         a3d.encoder3D(a3d.presets.MODELNET_ENCODER)
     with pytest.raises(KeyError):
         a3d.encoder3D({'name': 'x'})
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/a3d.h is the C-ABI contract: it must compile as C99 with no C++ or CUDA types in the signatures."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if not gcc:
+        pytest.skip('gcc not available')
+    src = tmp_path / 'use_a3d.c'
+    src.write_text('#include "a3d.h"\n'
+                   'int main(void) { a3d_desc d; a3d_enc2d_desc e; a3d_enc3d_desc v;\n'
+                   '  int (*f0)(void) = a3d_abi_version;\n'
+                   '  int (*f1)(a3d_enc2d*, const void*, int, int64_t, void*, int, void*) = a3d_enc2d_forward;\n'
+                   '  int (*f2)(a3d_enc3d*, const float*, int64_t, float*, void*) = a3d_enc3d_forward;\n'
+                   '  (void)d; (void)e; (void)v; (void)f0; (void)f1; (void)f2; return 0; }\n')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-fsyntax-only', '-I', os.path.join(ROOT, 'include'),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
