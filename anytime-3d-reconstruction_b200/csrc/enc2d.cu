@@ -65,6 +65,12 @@ struct a3d_enc2d {
   int64_t launches = 0;
   int64_t last_n = 0;
   int sticky = 0;
+  // host-call pipeline (a3d_enc2d_forward_host): two device input stages, a copy stream and a compute stream
+  cudaStream_t hs_compute = nullptr, hs_copy = nullptr;
+  cudaEvent_t hs_copied[2] = {nullptr, nullptr}, hs_consumed[2] = {nullptr, nullptr};
+  float* hs_in[2] = {nullptr, nullptr};
+  float* hs_out = nullptr;
+  int64_t hs_out_n = 0;
   bool no_p4 = false;         // A3D_ENC_P4=0: keep the shuffle pool in the resident-weight variant (cross-check)
   bool no_rh = false;         // A3D_ENC_RH=0: disable the resident-weight conv variant (cross-check)
   bool first_simt = false;    // A3D_ENC_FIRST=simt: CUDA-core image layer (diagnostic cross-check of the tensor-core one)
@@ -409,6 +415,14 @@ void a3d_enc2d_destroy(a3d_enc2d* h) {
   cudaDeviceSynchronize();
   for (auto& b : h->bufs) cudaFree(b.ptr);
   for (auto& op : h->ops) { cudaFree(op.wgt); cudaFree(op.wgt_first16); cudaFree(op.scale); cudaFree(op.shift); }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->hs_in[i]);
+    if (h->hs_copied[i]) cudaEventDestroy(h->hs_copied[i]);
+    if (h->hs_consumed[i]) cudaEventDestroy(h->hs_consumed[i]);
+  }
+  cudaFree(h->hs_out);
+  if (h->hs_compute) cudaStreamDestroy(h->hs_compute);
+  if (h->hs_copy) cudaStreamDestroy(h->hs_copy);
   delete h;
 }
 
@@ -469,6 +483,66 @@ int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n,
     rc = run_chunk(h, reinterpret_cast<const uint8_t*>(in_dev) + off * in_per, in_dtype, nc,
                    reinterpret_cast<uint8_t*>(out_dev) + off * out_per, out_dtype, st);
     if ((rc = sticky(h, rc))) return rc;
+  }
+  return A3D_OK;
+}
+
+int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, float* out_dev_or_null, float* out_host_or_null) {
+  int rc = check(h);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!images_host || (!out_dev_or_null && !out_host_or_null)))) {
+    set_error("a3d_enc2d_forward_host: bad arguments");
+    return A3D_ERR_INVALID;
+  }
+  if (n == 0) return A3D_OK;
+  if ((rc = sticky(h, finalize(h)))) return rc;
+  const size_t in_per = (size_t)h->desc.in_h * h->desc.in_w * h->desc.in_ch;       // fp32 elements per image
+  const size_t out_per = (size_t)h->out_h * h->out_w * h->out_c;
+  const int64_t mb = h->desc.max_batch;
+  if (!h->hs_compute) {
+    A3D_CUDA_OK(cudaStreamCreateWithFlags(&h->hs_compute, cudaStreamNonBlocking));
+    A3D_CUDA_OK(cudaStreamCreateWithFlags(&h->hs_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      A3D_CUDA_OK(cudaEventCreateWithFlags(&h->hs_copied[i], cudaEventDisableTiming));
+      A3D_CUDA_OK(cudaEventCreateWithFlags(&h->hs_consumed[i], cudaEventDisableTiming));
+      A3D_CUDA_OK(cudaMalloc(&h->hs_in[i], (size_t)mb * in_per * 4));
+    }
+  }
+  float* out_dev = out_dev_or_null;
+  if (!out_dev) {
+    if (n > h->hs_out_n) {
+      cudaFree(h->hs_out);
+      h->hs_out = nullptr;
+      A3D_CUDA_OK(cudaMalloc(&h->hs_out, (size_t)n * out_per * 4));
+      h->hs_out_n = n;
+    }
+    out_dev = h->hs_out;
+  }
+  const int64_t chunks = (n + mb - 1) / mb;
+  auto copy_chunk = [&](int64_t c) -> int {
+    const int b = (int)(c & 1);
+    const int64_t off = c * mb, nc = n - off < mb ? n - off : mb;
+    if (c >= 2) A3D_CUDA_OK(cudaStreamWaitEvent(h->hs_copy, h->hs_consumed[b], 0));   // stage b is free again
+    A3D_CUDA_OK(cudaMemcpyAsync(h->hs_in[b], images_host + off * in_per, (size_t)nc * in_per * 4, cudaMemcpyHostToDevice, h->hs_copy));
+    A3D_CUDA_OK(cudaEventRecord(h->hs_copied[b], h->hs_copy));
+    return A3D_OK;
+  };
+  if ((rc = copy_chunk(0))) return sticky(h, rc);
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t off = c * mb, nc = n - off < mb ? n - off : mb;
+    if (c + 1 < chunks && (rc = copy_chunk(c + 1))) return sticky(h, rc);               // overlaps the forward of chunk c
+    A3D_CUDA_OK(cudaStreamWaitEvent(h->hs_compute, h->hs_copied[b], 0));
+    if ((rc = sticky(h, run_chunk(h, h->hs_in[b], A3D_IO_F32, nc, out_dev + off * out_per, A3D_IO_F32, h->hs_compute)))) return rc;
+    A3D_CUDA_OK(cudaEventRecord(h->hs_consumed[b], h->hs_compute));
+  }
+  if (out_host_or_null)
+    A3D_CUDA_OK(cudaMemcpyAsync(out_host_or_null, out_dev, (size_t)n * out_per * 4, cudaMemcpyDeviceToHost, h->hs_compute));
+  cudaError_t e = cudaStreamSynchronize(h->hs_compute);
+  if (e != cudaSuccess) {
+    set_error("a3d_enc2d_forward_host: %s", cudaGetErrorString(e));
+    h->sticky = A3D_ERR_CUDA;
+    return A3D_ERR_CUDA;
   }
   return A3D_OK;
 }

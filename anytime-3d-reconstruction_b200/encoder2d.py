@@ -186,6 +186,8 @@ class Encoder2D:
         is_np = not isinstance(x, torch.Tensor)
         if is_np:
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if x.device.type == 'cpu' and out_dtype in ('fp32', 'f32', 'float32'):
+            return self._call_host(x.to(torch.float32).contiguous(), is_np)
         if x.dtype not in (torch.float32, self._tdtype) or self.input_shape[2] == 3:
             x = x.to(torch.float32)
         x = x.to(self.device).contiguous()
@@ -203,6 +205,26 @@ class Encoder2D:
         return out.cpu().numpy() if is_np else out
 
     predict = __call__
+
+    def _call_host(self, x, is_np: bool):
+        """Host images (numpy / CPU tensor, pinned or pageable) through a3d_enc2d_forward_host: chunks of max_batch with
+        the H2D copy of chunk i+1 overlapping the forward of chunk i.  numpy in -> numpy out, CPU tensor in -> CUDA out."""
+        torch = _torch()
+        if tuple(x.shape[1:]) != self.input_shape:
+            raise ValueError(f'expected input [N,{self.input_shape}], got {tuple(x.shape)}')
+        n = x.shape[0]
+        shape = (n, self._out_hwc[2]) if self._pooled else (n,) + self._out_hwc
+        if is_np:
+            out = np.empty(shape, np.float32)
+            out_dev, out_host = None, out.ctypes.data_as(C.c_void_p)
+        else:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+            out_dev, out_host = out.data_ptr(), None
+        with torch.cuda.device(self.device_index):
+            torch.cuda.current_stream().synchronize()      # the call runs on the handle's own streams
+            _capi.check(self._lib.a3d_enc2d_forward_host(self._h, x.data_ptr(), n, out_dev, out_host),
+                        'a3d_enc2d_forward_host')
+        return out
 
     def split_sample(self, enc_out, D: int, seed: int | None = None, obj_offset: int = 0, clip: float = 10.0):
         """nolbo.py:869-875: mean = out[:, :D]; logvar = clip(out[:, D:2D], -10, 10); z = sampling(mean, logvar).

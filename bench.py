@@ -178,7 +178,8 @@ def run_reference(args, rank, world):
 def config3_aux(a3d, dev, dtype, B=128, size=256, D16=16, steps=5):
     """Secondary measurement (not the headline metric): BASELINE config 3 -- Pascal3D image encoder + voxel decoder on
     synthetic RGB crops, batch 128, one GPU: Darknet19 + head2D -> mean / clipped logvar -> sampling -> decoder -> counts
-    (K = 1, full latent), random-init weights.  `value` with the images resident in HBM, `e2e` from numpy images."""
+    (K = 1, full latent), random-init weights.  `value` with the images resident in HBM, `e2e` from pinned host images
+    (100 MB H2D per step inside the timed region) to counts on the host."""
     import torch
     from oracle import anytime_ref as ar, decoder_ref as dr, encoder2d_ref as er
     layers = er.layer_list()
@@ -210,10 +211,22 @@ def config3_aux(a3d, dev, dtype, B=128, size=256, D16=16, steps=5):
 
     ms_enc, _ = timed(lambda i: enc(x))
     ms_all, c = timed(lambda i: step(x, i))
+    # e2e: images start in pinned host memory (bench contract); a second handle with max_batch = 32 lets the host path
+    # (a3d_enc2d_forward_host) overlap the H2D copy of chunk i+1 with the forward of chunk i
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    enc_h = a3d.image_encoder(a3d.presets.PASCAL_ENCODER_HEAD, input_size=(size, size), max_batch=32, operand_dtype=dtype)
+    enc_h.set_weights(enc.get_weights())
+
+    def step_host(i):
+        _, _, z = enc_h.encode(x_pin, D16, seed=100 + i)
+        return a3d.anytime_eval(dec, z, ones, None, bits, K=1, seed=i, fill='normal')['counts']
+    step_host(0).cpu()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(steps):
-        ce = step(x_host, i).cpu()
+        ce = step_host(i).cpu()
     e2e_s = (time.perf_counter() - t0) / steps
+    enc_h.close()
     alg, dense = er.encoder_macs(layers, size, size, 3)
     out = {'workload': f'Pascal3D multi-modal image encoder (Darknet19 + head2D, {size}x{size} RGB) + voxel decoder '
                        f'(D={D16}), batch {B}, K=1, synthetic crops, Keras-default random-init weights',

@@ -198,6 +198,12 @@ int a3d_enc2d_output_shape(const a3d_enc2d* h, int32_t* out_dims);
 int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n, void* out_dev, int out_dtype,
                       void* stream);
 
+/* Same model call with HOST images (what the reference's getEval holds: numpy batches from the loader,
+ * src/module/nolbo.py:855-869): fp32 NHWC images in host memory (pinned memory gives the full PCIe rate), processed in
+ * chunks of max_batch with the H2D copy of chunk i+1 overlapping the forward of chunk i on internal streams.  The
+ * result ([n, h*w*c] fp32) goes to out_dev (device pointer) and / or out_host; synchronous. */
+int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, float* out_dev_or_null, float* out_host_or_null);
+
 /* Latent split of the callers + sampling()  src/module/nolbo.py:869-875; src/module/function.py:35-38:
  * mean = enc_out[:, :D]; logvar = clip(enc_out[:, D:2D], -clip, clip); z = mean + sqrt(exp(logvar)) * eps,
  * eps ~ N(0,1) from Philox4x32-10 with counter (dim/4, 0x5A4D504C, obj_offset + b), key = seed (eps = 0 if

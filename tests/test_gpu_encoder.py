@@ -276,3 +276,20 @@ def test_empty_batch_and_smallest_image(a3d_mod):
     assert out.shape == (7, 32)
     assert np.abs(out - ref).max() < ENC_REL_TOL * max(np.abs(ref).max(), 1.0)
     enc.close()
+
+
+def test_host_image_path_matches_device_path(a3d_mod):
+    """a3d_enc2d_forward_host (numpy / pinned CPU tensors, chunked with copy / compute overlap) returns exactly what the
+    device-resident call returns."""
+    layers = er.layer_list()
+    ws = er.keras_default_weights(layers, 3, seed=31)
+    enc = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(64, 64), max_batch=3)
+    enc.set_weights(ws)
+    x = _images(64, 8, 14)                                   # 8 images, max_batch 3: chunks of 3 / 3 / 2
+    dev = enc(torch.from_numpy(x).cuda()).cpu().numpy()      # device-resident input
+    host = enc(x)                                            # numpy -> numpy through the host pipeline
+    assert isinstance(host, np.ndarray) and np.array_equal(host, dev)
+    pinned = enc(torch.from_numpy(x).pin_memory())           # pinned CPU tensor -> CUDA tensor
+    assert pinned.is_cuda and np.array_equal(pinned.cpu().numpy(), dev)
+    assert enc(np.zeros((0, 64, 64, 3), np.float32)).shape == (0, 32)
+    enc.close()
