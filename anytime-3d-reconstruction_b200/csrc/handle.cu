@@ -364,16 +364,17 @@ int finalize_weights(a3d_handle* h) {
     r = enc(&h->tmap_w5, dt, 2, h->d_w5_16, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
-    // pair tail (tail_tc2.cu): B rows 0..31 = W[td,th,tap_w = pw+1] at n = (td*4+th)*2+pw; 32..47 = W[td,th,3]; 48..63 = W[td,th,0]
+    // pair tail (tail_tc2.cu): B rows n = blk * 16 + td * 4 + j with th = (j + 1) & 3 (h taps in the order 1, 2, 3, 0):
+    // blk 0 = tap_w 1 (pw = 0, delta_w = 0), blk 1 = tap_w 2 (pw = 1, delta_w = 0), blk 2 = tap_w 3, blk 3 = tap_w 0
     p16.assign((size_t)64 * 64, cvt16(0.f, fmt));
     for (int td = 0; td < 4; ++td)
-      for (int th = 0; th < 4; ++th) {
-        const int q = td * 4 + th;
+      for (int j = 0; j < 4; ++j) {
+        const int n = td * 4 + j, q = td * 4 + ((j + 1) & 3);
         for (int ci = 0; ci < 64; ++ci) {
-          p16[(size_t)(2 * q + 0) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 1) * 64 + ci], fmt);
-          p16[(size_t)(2 * q + 1) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 2) * 64 + ci], fmt);
-          p16[(size_t)(32 + q) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 3) * 64 + ci], fmt);
-          p16[(size_t)(48 + q) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 0) * 64 + ci], fmt);
+          p16[(size_t)(0 + n) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 1) * 64 + ci], fmt);
+          p16[(size_t)(16 + n) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 2) * 64 + ci], fmt);
+          p16[(size_t)(32 + n) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 3) * 64 + ci], fmt);
+          p16[(size_t)(48 + n) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 0) * 64 + ci], fmt);
         }
       }
     if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_pair))) return rc;

@@ -207,8 +207,12 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
           for (int pw = 0; pw < 2; ++pw) {
             const float o0 = zh[1][ph][pw] + ex[((0 * 2 + ph) * 2 + pw) * kPos + rm];
             const float o1 = zh[2][ph][pw] + ex[((1 * 2 + ph) * 2 + pw) * kPos + rp];
-            psum[(0 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o0)) : o0;
-            psum[(1 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o1)) : o1;
+            // final_sigmoid 1 (counts only): sigmoid(x) = 0.5 + 0.5 tanh(x / 2), sum the tanh terms (one MUFU each), the
+            // affine part is applied to the mean;  2 (probabilities / loss emitted): 1 / (1 + exp(-x))
+            psum[(0 * 2 + ph) * 2 + pw] += final_sigmoid == 1 ? ptx::tanh_approx(0.5f * o0)
+                                           : final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o0)) : o0;
+            psum[(1 * 2 + ph) * 2 + pw] += final_sigmoid == 1 ? ptx::tanh_approx(0.5f * o1)
+                                           : final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o1)) : o1;
           }
       }
       // ---- finalize the block: mean over K, threshold, compare with the target bits
@@ -221,7 +225,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constan
         const bool ok = (pd ? ld <= 6 : ld >= 1) && (ph ? lh <= 6 : lh >= 1) && (pw ? lw <= 6 : lw >= 1) &&
                         od >= 0 && od < 64 && oh >= 0 && oh < 64 && ow >= 0 && ow < 64;
         if (!ok) continue;
-        const float mval = psum[p] * invk;
+        const float mval = final_sigmoid == 1 ? fmaf(psum[p], 0.5f * invk, 0.5f) : psum[p] * invk;
         const size_t v = ((size_t)od * 64 + oh) * 64 + ow;
         if (mean_prob) mean_prob[(size_t)b * A3D_VOXELS + v] = mval;
         if (target_bits) {
@@ -272,8 +276,9 @@ int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4, tmap_w5, B, K, final_sigmoid, target_bits, thr, counts, mean_prob, gamma,
-                                        loss);
+    // sigmoid mode: 1 = tanh form for the counts-only path, 2 = exp form whenever probabilities or the loss are emitted
+    const int sig = !final_sigmoid ? 0 : (mean_prob || loss) ? 2 : 1;
+    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4, tmap_w5, B, K, sig, target_bits, thr, counts, mean_prob, gamma, loss);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };

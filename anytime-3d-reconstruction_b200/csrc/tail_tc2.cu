@@ -7,9 +7,13 @@
 //
 // A CTA block is 4 (w) x 8 (d) x 8 (h) input voxels of TWO consecutive samples of one object; GEMM rows are ordered
 // (w, sample, d, h), so M-tile m (128 rows) is exactly w-slice m of both samples.  ONE MMA per (tile, K step) with N = 64:
-//   columns  0..31  Za[(td, th, pw)]  = X . W[td, th, tap_w = pw + 1]        (delta_w = 0)
-//   columns 32..47  Zm[(td, th)]      = X . W[td, th, tap_w = 3]             (feeds output parity pw = 0 of slice m + 1)
-//   columns 48..63  Zp[(td, th)]      = X . W[td, th, tap_w = 0]             (feeds output parity pw = 1 of slice m - 1)
+//   columns  0..15  Za0[(td, j)]  = X . W[td, th(j), tap_w = 1]        (delta_w = 0, output parity pw = 0)
+//   columns 16..31  Za1[(td, j)]  = X . W[td, th(j), tap_w = 2]        (delta_w = 0, output parity pw = 1)
+//   columns 32..47  Zm[(td, j)]   = X . W[td, th(j), tap_w = 3]        (feeds output parity pw = 0 of slice m + 1)
+//   columns 48..63  Zp[(td, j)]   = X . W[td, th(j), tap_w = 0]        (feeds output parity pw = 1 of slice m - 1)
+// with th(j) = (j + 1) & 3, i.e. the h taps in the order 1, 2, 3, 0: (th 1, th 2) are the delta_h = 0 taps of output
+// parities ph = 0 / 1 and (th 3, th 0) their delta_h = -1 / +1 partners, so every epilogue add works on an aligned
+// register PAIR and is issued as one packed add.rn.f32x2 (FADD2): the epilogue is issue-bound, not FLOP-bound.
 // The w-axis col2im is then free: the accumulators of slices m - 1, m, m + 1 live in the SAME TMEM lanes, in different
 // column blocks, so the epilogue thread of (slice m, row r) simply loads Za from block m, Zm from block m - 1 and Zp
 // from block m + 1.  h axis by warp shuffles, d axis by one shared-memory exchange, as in tail_tc.cu.  Blocks advance by
@@ -40,10 +44,12 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r
 // a 64-thread named barrier per warp pair (ids 2..9) instead of a 512-thread barrier per sample
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
 
-template <int FMT>
+// SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 = sigmoid as
+// 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities or the BCE loss are emitted)
+template <int FMT, int SIG>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
-                 int K, int final_sigmoid, const uint8_t* __restrict__ target_bits, float thr,
+                 int K, const uint8_t* __restrict__ target_bits, float thr,
                  unsigned long long* __restrict__ counts, float* __restrict__ mean_prob, float gamma,
                  double* __restrict__ loss) {
   extern __shared__ uint8_t smem_raw[];
@@ -73,7 +79,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       ptx::mbar_init(&a_full[i], 1);
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&t_full[i], 1);
-      ptx::mbar_init(&t_empty[i], 32 * kEpiWarps);
+      ptx::mbar_init(&t_empty[i], kEpiWarps);
     }
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
@@ -150,99 +156,118 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     const int slot = rt >> 6, ld = (rt >> 3) & 7, lh = rt & 7, lw = m;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float invk = 1.f / (float)K;
-    const int rm = r - 8, rp = r + 8;          // d - 1 / d + 1 neighbours (same sample; only used where ld allows)
+    // d - 1 / d + 1 neighbours (same sample).  Rows at the d border of the block read their own slot instead: those sums
+    // only reach outputs that the `ok` mask below drops
+    const int rm = ld >= 1 ? r - 8 : r, rp = ld <= 6 ? r + 8 : r;
+    const uint64_t half2 = ptx::f2_pack(0.5f, 0.5f);
+    uint64_t* exq = reinterpret_cast<uint64_t*>(exD);   // exchange buffers as (ph = 0, ph = 1) pairs: [2][4][kRows]
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int64_t b = item / kItemsPerObj;
       const int blk = (int)(item % kItemsPerObj);
       const int aw = -1 + 3 * (blk % kBlocksW), ah = -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
       const int ad = -1 + 7 * (blk / (kBlocksW * kBlocksDH));
-      float psum[8];
+      // running sums over the K samples, [pd][pw] as (ph = 0, ph = 1) pairs; with the sigmoid: sums of tanh(logit / 2)
+      uint64_t psum[4];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) psum[p] = 0.f;
+      for (int p = 0; p < 4; ++p) psum[p] = 0ull;
       for (int kp = 0; kp < pairs; ++kp, ++it) {
         const int s = it & 1;
         ptx::mbar_wait(&t_full[s], (it >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t tblk = tmem_base + lane_base + s * 256;
-        uint32_t y[32];    // Za [td][th][pw]
-        uint32_t zm[16];   // Zm of slice m - 1 [td][th]  -> pw = 0
-        uint32_t zp[16];   // Zp of slice m + 1 [td][th]  -> pw = 1
-        ptx::tmem_ld16(tblk + m * 64, *reinterpret_cast<uint32_t(*)[16]>(&y[0]));
-        ptx::tmem_ld16(tblk + m * 64 + 16, *reinterpret_cast<uint32_t(*)[16]>(&y[16]));
+        uint32_t ya[2][16];   // Za [pw][td][j]
+        uint32_t zn[2][16];   // [0]: Zm of slice m - 1 -> pw = 0;  [1]: Zp of slice m + 1 -> pw = 1   [td][j]
+        ptx::tmem_ld16(tblk + m * 64, ya[0]);
+        ptx::tmem_ld16(tblk + m * 64 + 16, ya[1]);
         // slices outside the block: any in-range address (the values only reach outputs that are masked below)
-        ptx::tmem_ld16(tblk + (m > 0 ? m - 1 : 0) * 64 + 32, zm);
-        ptx::tmem_ld16(tblk + (m < 3 ? m + 1 : 3) * 64 + 48, zp);
+        ptx::tmem_ld16(tblk + (m > 0 ? m - 1 : 0) * 64 + 32, zn[0]);
+        ptx::tmem_ld16(tblk + (m < 3 ? m + 1 : 3) * 64 + 48, zn[1]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&t_empty[s]);   // accumulators are in registers: release the TMEM buffer
-        // ---- w axis: add the neighbours' contributions (register adds only)
-        float z[32];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   // accumulators are in registers: release the TMEM buffer
+        // ---- w axis (register pairs) and h axis (lanes are 8 consecutive h):
+        //      out_h[ph=0] = Z[th=1] + Z_{h-1}[th=3];  out_h[ph=1] = Z[th=2] + Z_{h+1}[th=0]
+        uint64_t zh[4][2];   // [td][pw] as (ph = 0, ph = 1)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          z[2 * q] = __uint_as_float(y[2 * q]) + __uint_as_float(zm[q]);
-          z[2 * q + 1] = __uint_as_float(y[2 * q + 1]) + __uint_as_float(zp[q]);
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int td = 0; td < 4; ++td) {
+            const uint32_t* y = &ya[pw][td * 4];
+            const uint32_t* n = &zn[pw][td * 4];
+            const uint64_t c = ptx::f2_add(ptx::f2_pack_bits(y[0], y[1]), ptx::f2_pack_bits(n[0], n[1]));   // th 1, 2
+            const uint64_t o = ptx::f2_add(ptx::f2_pack_bits(y[2], y[3]), ptx::f2_pack_bits(n[2], n[3]));   // th 3, 0
+            float o3, o0;
+            ptx::f2_unpack(o, o3, o0);
+            const float up = __shfl_up_sync(0xffffffffu, o3, 1);
+            const float dn = __shfl_down_sync(0xffffffffu, o0, 1);
+            zh[td][pw] = ptx::f2_add(c, ptx::f2_pack(up, dn));
+          }
+        // ---- d axis through shared memory (double buffered across pairs: one warp-pair sync per pair)
+        uint64_t* ex = exq + (it & 1) * (4 * kRows);
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          ex[(0 * 2 + pw) * kRows + r] = zh[3][pw];
+          ex[(1 * 2 + pw) * kRows + r] = zh[0][pw];
         }
-        // ---- h axis (lanes are 8 consecutive h): out_h[ph=0][j] = Z_j[th=1] + Z_{j-1}[th=3]; [ph=1] = Z_j[th=2] + Z_{j+1}[th=0]
-        float zh[4][2][2];  // [td][ph][pw]
-#pragma unroll
-        for (int td = 0; td < 4; ++td)
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            const float up = __shfl_up_sync(0xffffffffu, z[(td * 4 + 3) * 2 + pw], 1);
-            const float dn = __shfl_down_sync(0xffffffffu, z[(td * 4 + 0) * 2 + pw], 1);
-            zh[td][0][pw] = z[(td * 4 + 1) * 2 + pw] + up;
-            zh[td][1][pw] = z[(td * 4 + 2) * 2 + pw] + dn;
-          }
-        // ---- d axis through shared memory (double buffered across pairs: one block sync per pair)
-        float* ex = exD + (it & 1) * (8 * kRows);
-#pragma unroll
-        for (int ph = 0; ph < 2; ++ph)
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            ex[((0 * 2 + ph) * 2 + pw) * kRows + r] = zh[3][ph][pw];
-            ex[((1 * 2 + ph) * 2 + pw) * kRows + r] = zh[0][ph][pw];
-          }
         pair_sync(e >> 1);
 #pragma unroll
-        for (int ph = 0; ph < 2; ++ph)
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            const float o0 = zh[1][ph][pw] + (ld >= 1 ? ex[((0 * 2 + ph) * 2 + pw) * kRows + rm] : 0.f);
-            const float o1 = zh[2][ph][pw] + (ld <= 6 ? ex[((1 * 2 + ph) * 2 + pw) * kRows + rp] : 0.f);
-            psum[(0 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o0)) : o0;
-            psum[(1 * 2 + ph) * 2 + pw] += final_sigmoid ? __fdividef(1.f, 1.f + __expf(-o1)) : o1;
+        for (int pw = 0; pw < 2; ++pw) {
+          uint64_t o0 = ptx::f2_add(zh[1][pw], ex[(0 * 2 + pw) * kRows + rm]);
+          uint64_t o1 = ptx::f2_add(zh[2][pw], ex[(1 * 2 + pw) * kRows + rp]);
+          if constexpr (SIG == 1) {
+            float a0, a1, b0, b1;
+            ptx::f2_unpack(ptx::f2_mul(o0, half2), a0, a1);
+            ptx::f2_unpack(ptx::f2_mul(o1, half2), b0, b1);
+            o0 = ptx::f2_pack(ptx::tanh_approx(a0), ptx::tanh_approx(a1));
+            o1 = ptx::f2_pack(ptx::tanh_approx(b0), ptx::tanh_approx(b1));
+          } else if constexpr (SIG == 2) {
+            float a0, a1, b0, b1;
+            ptx::f2_unpack(o0, a0, a1);
+            ptx::f2_unpack(o1, b0, b1);
+            o0 = ptx::f2_pack(__fdividef(1.f, 1.f + __expf(-a0)), __fdividef(1.f, 1.f + __expf(-a1)));
+            o1 = ptx::f2_pack(__fdividef(1.f, 1.f + __expf(-b0)), __fdividef(1.f, 1.f + __expf(-b1)));
           }
+          psum[0 * 2 + pw] = ptx::f2_add(psum[0 * 2 + pw], o0);
+          psum[1 * 2 + pw] = ptx::f2_add(psum[1 * 2 + pw], o1);
+        }
       }
       // ---- combine the two sample slots (rows r and r + 64 of a tile) through shared memory, then finalize in slot 0
-      float* ex = exD + (it & 1) * (8 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
+      uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
       if (slot == 1) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) ex[p * kRows + r] = psum[p];
+        for (int p = 0; p < 4; ++p) ex[p * kRows + r] = psum[p];
       }
       epi_sync();
       int tp = 0, fp = 0, fn = 0;
       float lsum = 0.f;
       if (slot == 0) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
-          const int od = 2 * (ad + ld) + pd, oh = 2 * (ah + lh) + ph, ow = 2 * (aw + lw) + pw;
-          const bool ok = (pd ? ld <= 6 : ld >= 1) && (ph ? lh <= 6 : lh >= 1) && (pw ? lw <= 2 : lw >= 1) &&
-                          od >= 0 && od < 64 && oh >= 0 && oh < 64 && ow >= 0 && ow < 64;
-          if (!ok) continue;
-          const float mval = (psum[p] + ex[p * kRows + r + 64]) * invk;
-          const size_t v = ((size_t)od * 64 + oh) * 64 + ow;
-          if (mean_prob) mean_prob[(size_t)b * A3D_VOXELS + v] = mval;
-          if (target_bits) {
-            const int t = (target_bits[(size_t)b * (A3D_VOXELS / 8) + (v >> 3)] >> (v & 7)) & 1;
-            const int yv = mval >= thr;
-            tp += t & yv;
-            fp += (1 - t) & yv;
-            fn += t & (1 - yv);
-            if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
-              const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
-              lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
+        for (int q = 0; q < 4; ++q) {
+          float v2[2];
+          ptx::f2_unpack(ptx::f2_add(psum[q], ex[q * kRows + r + 64]), v2[0], v2[1]);
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {
+            const int pd = q >> 1, pw = q & 1;
+            const int od = 2 * (ad + ld) + pd, oh = 2 * (ah + lh) + ph, ow = 2 * (aw + lw) + pw;
+            const bool ok = (pd ? ld <= 6 : ld >= 1) && (ph ? lh <= 6 : lh >= 1) && (pw ? lw <= 2 : lw >= 1) &&
+                            od >= 0 && od < 64 && oh >= 0 && oh < 64 && ow >= 0 && ow < 64;
+            if (!ok) continue;
+            // mean of sigmoid = 0.5 + 0.5 * mean of tanh(logit / 2)
+            const float mval = SIG == 1 ? fmaf(v2[ph], 0.5f * invk, 0.5f) : v2[ph] * invk;
+            const size_t v = ((size_t)od * 64 + oh) * 64 + ow;
+            if (mean_prob) mean_prob[(size_t)b * A3D_VOXELS + v] = mval;
+            if (target_bits) {
+              const int t = (target_bits[(size_t)b * (A3D_VOXELS / 8) + (v >> 3)] >> (v & 7)) & 1;
+              const int yv = mval >= thr;
+              tp += t & yv;
+              fp += (1 - t) & yv;
+              fn += t & (1 - yv);
+              if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
+                const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
+                lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
+              }
             }
           }
         }
@@ -285,12 +310,18 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4p, tmap_w5p, B, K, final_sigmoid, target_bits, thr, counts, mean_prob, gamma,
-                                        loss);
+    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4p, tmap_w5p, B, K, target_bits, thr, counts, mean_prob, gamma, loss);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };
-  const int rc = fmt == A3D_DTYPE_F16 ? launch(tail_pair_kernel<A3D_DTYPE_F16>) : launch(tail_pair_kernel<A3D_DTYPE_BF16>);
+  const int sig = !final_sigmoid ? 0 : (mean_prob || loss) ? 2 : 1;
+  int rc;
+  if (fmt == A3D_DTYPE_F16)
+    rc = sig == 0 ? launch(tail_pair_kernel<A3D_DTYPE_F16, 0>)
+                  : sig == 1 ? launch(tail_pair_kernel<A3D_DTYPE_F16, 1>) : launch(tail_pair_kernel<A3D_DTYPE_F16, 2>);
+  else
+    rc = sig == 0 ? launch(tail_pair_kernel<A3D_DTYPE_BF16, 0>)
+                  : sig == 1 ? launch(tail_pair_kernel<A3D_DTYPE_BF16, 1>) : launch(tail_pair_kernel<A3D_DTYPE_BF16, 2>);
   if (rc == A3D_OK && launches) ++*launches;
   return rc;
 }
