@@ -435,8 +435,9 @@ int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, un
   if (h->desc.impl == A3D_IMPL_SIMT)
     return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss, st,
                        &h->launches);
-  // even K (configs 2 and 5): the pair kernel reads every activation tile once instead of three times
-  if (K >= 2 && (K & 1) == 0 && !h->tail_v3 && h->max_chunk >= 2)
+  // even K (configs 2 and 5) and K = 1 (configs 1, 3, 4: two consecutive objects per block): the pair kernel reads every
+  // activation tile once instead of three times
+  if ((K == 1 || (K & 1) == 0) && !h->tail_v3 && h->max_chunk >= 2)
     return launch_tail_pair(h->tmap_a4p, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
                             loss, h->num_sms, st, &h->launches);
   return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss,

@@ -19,6 +19,7 @@
 // from block m + 1.  h axis by warp shuffles, d axis by one shared-memory exchange, as in tail_tc.cu.  Blocks advance by
 // 3 slices in w (6 complete output columns) and by 7 voxels in d and h (14 complete outputs).
 #include <cstdlib>
+#include <type_traits>
 
 #include "cvt.cuh"
 #include "internal.h"
@@ -46,7 +47,9 @@ __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0,
 
 // SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 = sigmoid as
 // 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities or the BCE loss are emitted)
-template <int FMT, int SIG>
+// K1: K == 1 -- the two row slots hold two CONSECUTIVE OBJECTS (2j, 2j + 1) instead of two samples of one object; no
+// slot combine and no block-wide barrier, every slot finalizes its own object.
+template <int FMT, int SIG, bool K1>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
                  int K, const uint8_t* __restrict__ target_bits, float thr,
@@ -67,8 +70,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t total_items = B * kItemsPerObj;
-  const int pairs = K >> 1;         // K is even (the launcher falls back to tail_tc.cu otherwise)
+  const int64_t total_items = (K1 ? (B + 1) / 2 : B) * kItemsPerObj;
+  const int pairs = K1 ? 1 : K >> 1;   // K is 1 or even (the launcher falls back to tail_tc.cu otherwise)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a4);
@@ -112,7 +115,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&a_full[s], kABytes);
           // tensor-map dims are (c, h, d, n, w): rows land as (w, sample, d, h) with h fastest
-          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, (int)(b * K + 2 * kp), aw);
+          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, (int)(K1 ? 2 * b : b * K + 2 * kp), aw);
         }
         __syncwarp();
       }
@@ -233,64 +236,77 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           psum[1 * 2 + pw] = ptx::f2_add(psum[1 * 2 + pw], o1);
         }
       }
-      // ---- combine the two sample slots (rows r and r + 64 of a tile) through shared memory, then finalize in slot 0
-      uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
-      if (slot == 1) {
+      // ---- K >= 2: combine the two sample slots (rows r and r + 64 of a tile) through shared memory and finalize in
+      //      slot 0;  K == 1: each slot finalizes its own object.  `slot` is uniform per warp.
+      const int64_t obj = K1 ? 2 * b + slot : b;
+      bool fin;
+      if constexpr (K1) {
+        fin = obj < B;
+      } else {
+        uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
+        if (slot == 1) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) ex[p * kRows + r] = psum[p];
+          for (int p = 0; p < 4; ++p) ex[p * kRows + r] = psum[p];
+        }
+        epi_sync();
+        fin = slot == 0;
+        if (fin) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) psum[p] = ptx::f2_add(psum[p], ex[p * kRows + r + 64]);
+        }
       }
-      epi_sync();
-      int tp = 0, fp = 0, fn = 0;
-      float lsum = 0.f;
-      if (slot == 0) {
+      if (fin) {
+        // this row's 2 x 2 x 2 outputs: od = 2 * d0 + pd, ...; an output is complete when the neighbour row on that side is
+        // inside the block (or the output itself lies outside the grid and is dropped)
+        const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
+        const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
+        const bool okd[2] = {ind && ld >= 1, ind && ld <= 6};
+        const bool okh[2] = {inh && lh >= 1, inh && lh <= 6};
+        const bool okw[2] = {inw && lw >= 1, inw && lw <= 2};
+        const int vbase = (2 * d0 * 64 + 2 * h0) * 64 + 2 * w0;
+        const int bit0 = (2 * w0) & 7;
+        uint32_t packed = 0;   // tp | fp << 10 | fn << 20 (a warp adds at most 256 per field)
+        float lsum = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v2[2];
-          ptx::f2_unpack(ptx::f2_add(psum[q], ex[q * kRows + r + 64]), v2[0], v2[1]);
+        for (int pd = 0; pd < 2; ++pd)
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
-            const int pd = q >> 1, pw = q & 1;
-            const int od = 2 * (ad + ld) + pd, oh = 2 * (ah + lh) + ph, ow = 2 * (aw + lw) + pw;
-            const bool ok = (pd ? ld <= 6 : ld >= 1) && (ph ? lh <= 6 : lh >= 1) && (pw ? lw <= 2 : lw >= 1) &&
-                            od >= 0 && od < 64 && oh >= 0 && oh < 64 && ow >= 0 && ow < 64;
-            if (!ok) continue;
-            // mean of sigmoid = 0.5 + 0.5 * mean of tanh(logit / 2)
-            const float mval = SIG == 1 ? fmaf(v2[ph], 0.5f * invk, 0.5f) : v2[ph] * invk;
-            const size_t v = ((size_t)od * 64 + oh) * 64 + ow;
-            if (mean_prob) mean_prob[(size_t)b * A3D_VOXELS + v] = mval;
-            if (target_bits) {
-              const int t = (target_bits[(size_t)b * (A3D_VOXELS / 8) + (v >> 3)] >> (v & 7)) & 1;
-              const int yv = mval >= thr;
-              tp += t & yv;
-              fp += (1 - t) & yv;
-              fn += t & (1 - yv);
-              if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
-                const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
-                lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
+            if (!(okd[pd] && okh[ph] && (okw[0] || okw[1]))) continue;
+            const int v0 = vbase + pd * 4096 + ph * 64;     // voxel index of the pw = 0 output; pw = 1 is the next bit
+            const uint32_t byte = target_bits ? target_bits[(size_t)obj * (A3D_VOXELS / 8) + (v0 >> 3)] : 0u;
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw) {
+              if (!okw[pw]) continue;
+              float v2[2];
+              ptx::f2_unpack(psum[pd * 2 + pw], v2[0], v2[1]);
+              // mean of sigmoid = 0.5 + 0.5 * mean of tanh(logit / 2)
+              const float mval = SIG == 1 ? fmaf(v2[ph], 0.5f * invk, 0.5f) : v2[ph] * invk;
+              if (mean_prob) mean_prob[(size_t)obj * A3D_VOXELS + v0 + pw] = mval;
+              if (target_bits) {
+                const uint32_t t = (byte >> (bit0 + pw)) & 1u;
+                const uint32_t yv = mval >= thr;
+                packed += (t & yv) + (((t ^ 1u) & yv) << 10) + ((t & (yv ^ 1u)) << 20);
+                if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
+                  const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
+                  lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
+                }
               }
             }
           }
+        if (target_bits) {
+          if (loss) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            if (lane == 0 && lsum != 0.f) atomicAdd(loss + obj, (double)lsum);
+          }
+          packed = __reduce_add_sync(0xffffffffu, packed);
+          if (lane < 3) {
+            const uint32_t f = (packed >> (10 * lane)) & 1023u;
+            if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
+          }
         }
       }
-      if (target_bits) {
-        if (loss) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-          if (lane == 0 && lsum != 0.f) atomicAdd(loss + b, (double)lsum);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          tp += __shfl_xor_sync(0xffffffffu, tp, o);
-          fp += __shfl_xor_sync(0xffffffffu, fp, o);
-          fn += __shfl_xor_sync(0xffffffffu, fn, o);
-        }
-        if (lane == 0) {
-          if (tp) atomicAdd(counts + b * 3 + 0, (unsigned long long)tp);
-          if (fp) atomicAdd(counts + b * 3 + 1, (unsigned long long)fp);
-          if (fn) atomicAdd(counts + b * 3 + 2, (unsigned long long)fn);
-        }
-      }
-      epi_sync();   // the slot exchange buffer is reused by the next item's d-exchange
+      if constexpr (!K1) epi_sync();   // the slot exchange buffer is reused by the next item's d-exchange
     }
   }
 
@@ -305,8 +321,8 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
                      int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
                      float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches) {
   if (B <= 0) return A3D_OK;
-  if (K < 2 || (K & 1)) { set_error("tail_pair: K must be even"); return A3D_ERR_INVALID; }
-  const int64_t items = B * kItemsPerObj;
+  if (K != 1 && (K & 1)) { set_error("tail_pair: K must be 1 or even"); return A3D_ERR_INVALID; }
+  const int64_t items = (K == 1 ? (B + 1) / 2 : B) * kItemsPerObj;
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -315,13 +331,19 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
     return A3D_OK;
   };
   const int sig = !final_sigmoid ? 0 : (mean_prob || loss) ? 2 : 1;
+  auto pick = [&](auto fmt_c, auto k1_c) -> int {
+    constexpr int F = decltype(fmt_c)::value;
+    constexpr bool O = decltype(k1_c)::value;
+    return sig == 0 ? launch(tail_pair_kernel<F, 0, O>)
+                    : sig == 1 ? launch(tail_pair_kernel<F, 1, O>) : launch(tail_pair_kernel<F, 2, O>);
+  };
+  using F16 = std::integral_constant<int, A3D_DTYPE_F16>;
+  using BF16 = std::integral_constant<int, A3D_DTYPE_BF16>;
   int rc;
   if (fmt == A3D_DTYPE_F16)
-    rc = sig == 0 ? launch(tail_pair_kernel<A3D_DTYPE_F16, 0>)
-                  : sig == 1 ? launch(tail_pair_kernel<A3D_DTYPE_F16, 1>) : launch(tail_pair_kernel<A3D_DTYPE_F16, 2>);
+    rc = K == 1 ? pick(F16{}, std::true_type{}) : pick(F16{}, std::false_type{});
   else
-    rc = sig == 0 ? launch(tail_pair_kernel<A3D_DTYPE_BF16, 0>)
-                  : sig == 1 ? launch(tail_pair_kernel<A3D_DTYPE_BF16, 1>) : launch(tail_pair_kernel<A3D_DTYPE_BF16, 2>);
+    rc = K == 1 ? pick(BF16{}, std::true_type{}) : pick(BF16{}, std::false_type{});
   if (rc == A3D_OK && launches) ++*launches;
   return rc;
 }

@@ -283,6 +283,33 @@ def test_k_copies_of_one_latent_equal_single_decode(a3d_mod, decoders):
     assert np.array_equal(single, b['mean_prob'].cpu().numpy())
 
 
+@pytest.mark.parametrize('B,K,chunk', [(37, 1, 32), (33, 1, 32), (3, 2, 32), (1, 1, 32)])
+def test_pair_tail_matches_previous_tail_kernel(a3d_mod, weights, B, K, chunk, monkeypatch):
+    """K = 1 puts two consecutive OBJECTS into the two row slots of the pair tail (odd batches leave the second slot of the
+    last block of a chunk masked: 32 + 5 and 32 + 1 objects); the three-view kernel (A3D_TAIL_IMPL=v3, read when the handle is created) is the cross-check."""
+    ws = weights[('mn', 'trained')]
+    rng = np.random.default_rng(100 + B)
+    zc = rng.standard_normal((B, K, 64)).astype(np.float32)
+    tgt = ar.make_targets(rng, B)
+    new = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=chunk)
+    monkeypatch.setenv('A3D_TAIL_IMPL', 'v3')
+    old = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=chunk)
+    monkeypatch.delenv('A3D_TAIL_IMPL')
+    new.set_weights(ws)
+    old.set_weights(ws)
+    a = a3d_mod.anytime_eval(new, None, None, None, tgt, z_completed=zc, return_grid=True)
+    b = a3d_mod.anytime_eval(old, None, None, None, tgt, z_completed=zc, return_grid=True)
+    assert (a['mean_prob'] - b['mean_prob']).abs().max().item() < 1e-6
+    nflip = int(((a['mean_prob'] >= 0.5) != (b['mean_prob'] >= 0.5)).sum().item())
+    assert (a['counts'] - b['counts']).abs().sum().item() <= 2 * nflip
+    # counts-only path (tanh form of the sigmoid): same integers up to voxels whose mean sits within 1e-6 of the threshold
+    c = a3d_mod.anytime_eval(new, None, None, None, ar.pack_bits(tgt), z_completed=zc)
+    near = int(((a['mean_prob'] - 0.5).abs() < 1e-6).sum().item())
+    assert (c['counts'] - a['counts']).abs().sum().item() <= 2 * near
+    mp = a['mean_prob'].reshape(B, -1)
+    assert torch.equal(a['counts'][:, 0] + a['counts'][:, 1], (mp >= 0.5).sum(1))
+
+
 def test_getEval_reference_return_tuple(a3d_mod, decoders):
     dec = decoders[('mn', 'trained')]
     rng = np.random.default_rng(8)
