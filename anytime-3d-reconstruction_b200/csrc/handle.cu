@@ -94,6 +94,8 @@ struct a3d_handle {
   CUtensorMap tmap_a4, tmap_w5;                                                // tail: (c,w,h,d,n) view of act[4]; W5
   void* d_w5_pair = nullptr;                                                   // pair tail (tail_tc2.cu): [Za 32 | Zm 16 | Zp 16] rows
   CUtensorMap tmap_a4p, tmap_w5p;                                              // pair tail: (c,h,d,n,w) view of act[4]; its W5
+  CUtensorMap tmap_a4h;                                                        // same view, 64 x 32 x 4 x 1 x 4 boxes (HCOL mode)
+  bool tail_pair = false;                                                      // A3D_TAIL_IMPL=pair: 4 x 8 x 8 x 2-sample blocks
   bool tail_v3 = false;                                                        // A3D_TAIL_IMPL=v3: always use tail_tc.cu
   // arena
   int64_t max_chunk = 0;
@@ -384,6 +386,10 @@ int finalize_weights(a3d_handle* h) {
     r = enc(&h->tmap_a4p, dt, 5, h->act[4], pd, ps, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pair-tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    cuuint32_t hb[5] = {64, 32, 4, 1, 4};   // HCOL mode: rows (w, d, h) of one sample, the whole h axis per box
+    r = enc(&h->tmap_a4h, dt, 5, h->act[4], pd, ps, hb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(hcol-tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
     cuuint64_t wpd[2] = {64, 64};
     cuuint32_t wpb[2] = {64, 64};
     r = enc(&h->tmap_w5p, dt, 2, h->d_w5_pair, wpd, ws, wpb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -435,11 +441,14 @@ int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, un
   if (h->desc.impl == A3D_IMPL_SIMT)
     return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss, st,
                        &h->launches);
-  // even K (configs 2 and 5) and K = 1 (configs 1, 3, 4: two consecutive objects per block): the pair kernel reads every
-  // activation tile once instead of three times
+  // default: one-sample blocks with the whole h axis per tile (any K).  A3D_TAIL_IMPL=pair: the two-sample / two-object
+  // blocks (even K, K = 1); A3D_TAIL_IMPL=v3 or odd K >= 3 under "pair": the three-view kernel of tail_tc.cu
+  if (!h->tail_v3 && !h->tail_pair)
+    return launch_tail_pair(h->tmap_a4h, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
+                            loss, h->num_sms, true, st, &h->launches);
   if ((K == 1 || (K & 1) == 0) && !h->tail_v3 && h->max_chunk >= 2)
     return launch_tail_pair(h->tmap_a4p, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
-                            loss, h->num_sms, st, &h->launches);
+                            loss, h->num_sms, false, st, &h->launches);
   return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss,
                         h->num_sms, st, &h->launches);
 }
@@ -533,7 +542,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
   { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = e && std::string(e) == "generic"; }
-  { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; }
+  { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; h->tail_pair = e && std::string(e) == "pair"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
   h->act_elems[0] = 512; h->act_elems[1] = 64 * 512; h->act_elems[2] = 512 * 256; h->act_elems[3] = 4096 * 128;

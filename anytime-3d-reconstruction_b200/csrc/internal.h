@@ -74,7 +74,8 @@ int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64
 // pair variant (tail_tc2.cu, even K): tmap_a4p = (c,h,d,n,w) view with box (64,8,8,2,4); tmap_w5p = 64-row weight tile
 int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, int64_t B, int K, int fmt,
                      int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                     float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches);
+                     float* mean_prob, float gamma, double* loss, int num_sms, bool hcol, cudaStream_t st,
+                     int64_t* launches);
 int launch_binary_loss(const float* pred, const float* target, int64_t B, int64_t V, float gamma, double* loss,
                        cudaStream_t st, int64_t* launches);
 int launch_counts_sweep(const float* target, const float* pred, int64_t B, int64_t V, const float* thr, int T, int strict,

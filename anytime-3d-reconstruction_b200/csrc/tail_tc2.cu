@@ -31,7 +31,14 @@ namespace {
 constexpr int kBw = 4, kBd = 8, kBh = 8;
 constexpr int kRows = kBw * 2 * kBd * kBh;       // 512 GEMM rows = 4 M-tiles of 128
 constexpr int kBlocksW = 11, kBlocksDH = 5;      // w origins -1 + 3i (i < 11), d / h origins -1 + 7i (i < 5)
-constexpr int kItemsPerObj = kBlocksW * kBlocksDH * kBlocksDH;
+constexpr int kItemsPair = kBlocksW * kBlocksDH * kBlocksDH;   // 275 blocks of 4 x 8 x 8 x 2 samples
+constexpr int kBlocksD4 = 11;                                   // HCOL: d origins -1 + 3i (i < 11), h complete
+constexpr int kItemsHcol = kBlocksW * kBlocksD4;                // 121 blocks of 4 (w) x 4 (d) x 32 (h) x 1 sample
+// MODE_PAIR: two samples of one object per block (even K);  MODE_PAIR1: K = 1, two consecutive objects per block;
+// MODE_HCOL: one sample per block, tile rows = (d 4, h 32): the whole h axis sits in the 32 lanes of a warp, so there is
+// no h halo (61,952 instead of 70,400 rows per decode cross the L2->SM fabric, which is what bounds this kernel) and any
+// K works; the d exchange couples the four warps of a tile (128-thread named barrier).
+enum { MODE_PAIR = 0, MODE_PAIR1 = 1, MODE_HCOL = 2 };
 constexpr int kABytes = kRows * 128;             // 64 KB per stage
 constexpr int kWRows = 64;
 constexpr int kWBytes = kWRows * 128;
@@ -44,12 +51,13 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r
 // The d-axis exchange only couples rows r and r +- 8 of one 64-row (d, h) plane group = the two epilogue warps 2j, 2j + 1:
 // a 64-thread named barrier per warp pair (ids 2..9) instead of a 512-thread barrier per sample
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
+__device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory"); }
 
 // SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 = sigmoid as
 // 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities or the BCE loss are emitted)
-// K1: K == 1 -- the two row slots hold two CONSECUTIVE OBJECTS (2j, 2j + 1) instead of two samples of one object; no
-// slot combine and no block-wide barrier, every slot finalizes its own object.
-template <int FMT, int SIG, bool K1>
+// MODE_PAIR1: K == 1 -- the two row slots hold two CONSECUTIVE OBJECTS (2j, 2j + 1) instead of two samples of one object;
+// no slot combine and no block-wide barrier, every slot finalizes its own object.
+template <int FMT, int SIG, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
                  int K, const uint8_t* __restrict__ target_bits, float thr,
@@ -70,8 +78,10 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool K1 = MODE == MODE_PAIR1, HCOL = MODE == MODE_HCOL;
+  constexpr int kItemsPerObj = HCOL ? kItemsHcol : kItemsPair;
   const int64_t total_items = (K1 ? (B + 1) / 2 : B) * kItemsPerObj;
-  const int pairs = K1 ? 1 : K >> 1;   // K is 1 or even (the launcher falls back to tail_tc.cu otherwise)
+  const int pairs = K1 ? 1 : HCOL ? K : K >> 1;   // block iterations per item
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a4);
@@ -107,15 +117,15 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int64_t b = item / kItemsPerObj;
       const int blk = (int)(item % kItemsPerObj);
-      const int aw = -1 + 3 * (blk % kBlocksW), ah = -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
-      const int ad = -1 + 7 * (blk / (kBlocksW * kBlocksDH));
+      const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
+      const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
       for (int kp = 0; kp < pairs; ++kp, ++it) {
         const int s = it & 1;
         ptx::mbar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&a_full[s], kABytes);
-          // tensor-map dims are (c, h, d, n, w): rows land as (w, sample, d, h) with h fastest
-          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, (int)(K1 ? 2 * b : b * K + 2 * kp), aw);
+          // tensor-map dims are (c, h, d, n, w): rows land as (w, sample, d, h) with h fastest (HCOL: box 64 x 32 x 4 x 1 x 4)
+          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, (int)(K1 ? 2 * b : HCOL ? b * K + kp : b * K + 2 * kp), aw);
         }
         __syncwarp();
       }
@@ -156,20 +166,23 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     const int quarter = e & 3;                 // TMEM lane quarter == warp % 4
     const int rt = quarter * 32 + lane;        // row in the tile: sample * 64 + ld * 8 + lh
     const int r = m * 128 + rt;                // row in the block
-    const int slot = rt >> 6, ld = (rt >> 3) & 7, lh = rt & 7, lw = m;
+    const int slot = HCOL ? 0 : rt >> 6, ld = HCOL ? quarter : (rt >> 3) & 7, lh = HCOL ? lane : rt & 7, lw = m;
+    constexpr int kDStep = HCOL ? 32 : 8, kDLast = HCOL ? 3 : 7;   // rows between d neighbours; last d index of a tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float invk = 1.f / (float)K;
     // d - 1 / d + 1 neighbours (same sample).  Rows at the d border of the block read their own slot instead: those sums
     // only reach outputs that the `ok` mask below drops
-    const int rm = ld >= 1 ? r - 8 : r, rp = ld <= 6 ? r + 8 : r;
+    const int rm = ld >= 1 ? r - kDStep : r, rp = ld < kDLast ? r + kDStep : r;
+    // HCOL: lanes 0 / 31 sit on the grid border in h, their missing neighbour is the zero padding
+    const uint64_t hmask = ptx::f2_pack(!HCOL || lane >= 1 ? 1.f : 0.f, !HCOL || lane <= 30 ? 1.f : 0.f);
     const uint64_t half2 = ptx::f2_pack(0.5f, 0.5f);
     uint64_t* exq = reinterpret_cast<uint64_t*>(exD);   // exchange buffers as (ph = 0, ph = 1) pairs: [2][4][kRows]
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int64_t b = item / kItemsPerObj;
       const int blk = (int)(item % kItemsPerObj);
-      const int aw = -1 + 3 * (blk % kBlocksW), ah = -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
-      const int ad = -1 + 7 * (blk / (kBlocksW * kBlocksDH));
+      const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
+      const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
       // running sums over the K samples, [pd][pw] as (ph = 0, ph = 1) pairs; with the sigmoid: sums of tanh(logit / 2)
       uint64_t psum[4];
 #pragma unroll
@@ -205,7 +218,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             ptx::f2_unpack(o, o3, o0);
             const float up = __shfl_up_sync(0xffffffffu, o3, 1);
             const float dn = __shfl_down_sync(0xffffffffu, o0, 1);
-            zh[td][pw] = ptx::f2_add(c, ptx::f2_pack(up, dn));
+            if constexpr (HCOL) zh[td][pw] = ptx::f2_fma(ptx::f2_pack(up, dn), hmask, c);
+            else zh[td][pw] = ptx::f2_add(c, ptx::f2_pack(up, dn));
           }
         // ---- d axis through shared memory (double buffered across pairs: one warp-pair sync per pair)
         uint64_t* ex = exq + (it & 1) * (4 * kRows);
@@ -214,7 +228,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           ex[(0 * 2 + pw) * kRows + r] = zh[3][pw];
           ex[(1 * 2 + pw) * kRows + r] = zh[0][pw];
         }
-        pair_sync(e >> 1);
+        if constexpr (HCOL) tile_sync(m);
+        else pair_sync(e >> 1);
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw) {
           uint64_t o0 = ptx::f2_add(zh[1][pw], ex[(0 * 2 + pw) * kRows + rm]);
@@ -242,6 +257,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       bool fin;
       if constexpr (K1) {
         fin = obj < B;
+      } else if constexpr (HCOL) {
+        fin = true;
       } else {
         uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
         if (slot == 1) {
@@ -260,8 +277,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
         // inside the block (or the output itself lies outside the grid and is dropped)
         const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
         const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
-        const bool okd[2] = {ind && ld >= 1, ind && ld <= 6};
-        const bool okh[2] = {inh && lh >= 1, inh && lh <= 6};
+        const bool okd[2] = {ind && ld >= 1, ind && ld < kDLast};
+        const bool okh[2] = {inh && (HCOL || lh >= 1), inh && (HCOL || lh <= 6)};
         const bool okw[2] = {inw && lw >= 1, inw && lw <= 2};
         const int vbase = (2 * d0 * 64 + 2 * h0) * 64 + 2 * w0;
         const int bit0 = (2 * w0) & 7;
@@ -306,7 +323,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           }
         }
       }
-      if constexpr (!K1) epi_sync();   // the slot exchange buffer is reused by the next item's d-exchange
+      if constexpr (MODE == MODE_PAIR) epi_sync();   // the slot exchange buffer is reused by the next item's d-exchange
     }
   }
 
@@ -319,10 +336,12 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
 
 int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, int64_t B, int K, int fmt,
                      int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                     float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches) {
+                     float* mean_prob, float gamma, double* loss, int num_sms, bool hcol, cudaStream_t st,
+                     int64_t* launches) {
   if (B <= 0) return A3D_OK;
-  if (K != 1 && (K & 1)) { set_error("tail_pair: K must be 1 or even"); return A3D_ERR_INVALID; }
-  const int64_t items = (K == 1 ? (B + 1) / 2 : B) * kItemsPerObj;
+  if (!hcol && K != 1 && (K & 1)) { set_error("tail_pair: K must be 1 or even"); return A3D_ERR_INVALID; }
+  const int mode = hcol ? MODE_HCOL : K == 1 ? MODE_PAIR1 : MODE_PAIR;
+  const int64_t items = mode == MODE_HCOL ? B * kItemsHcol : (mode == MODE_PAIR1 ? (B + 1) / 2 : B) * kItemsPair;
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -330,20 +349,21 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };
+  // sigmoid mode: 1 = tanh form for the counts-only path, 2 = exp form whenever probabilities or the loss are emitted
   const int sig = !final_sigmoid ? 0 : (mean_prob || loss) ? 2 : 1;
-  auto pick = [&](auto fmt_c, auto k1_c) -> int {
+  auto pick = [&](auto fmt_c, auto mode_c) -> int {
     constexpr int F = decltype(fmt_c)::value;
-    constexpr bool O = decltype(k1_c)::value;
-    return sig == 0 ? launch(tail_pair_kernel<F, 0, O>)
-                    : sig == 1 ? launch(tail_pair_kernel<F, 1, O>) : launch(tail_pair_kernel<F, 2, O>);
+    constexpr int M = decltype(mode_c)::value;
+    return sig == 0 ? launch(tail_pair_kernel<F, 0, M>)
+                    : sig == 1 ? launch(tail_pair_kernel<F, 1, M>) : launch(tail_pair_kernel<F, 2, M>);
   };
-  using F16 = std::integral_constant<int, A3D_DTYPE_F16>;
-  using BF16 = std::integral_constant<int, A3D_DTYPE_BF16>;
-  int rc;
-  if (fmt == A3D_DTYPE_F16)
-    rc = K == 1 ? pick(F16{}, std::true_type{}) : pick(F16{}, std::false_type{});
-  else
-    rc = K == 1 ? pick(BF16{}, std::true_type{}) : pick(BF16{}, std::false_type{});
+  auto pick_mode = [&](auto fmt_c) -> int {
+    return mode == MODE_HCOL ? pick(fmt_c, std::integral_constant<int, MODE_HCOL>{})
+                             : mode == MODE_PAIR1 ? pick(fmt_c, std::integral_constant<int, MODE_PAIR1>{})
+                                                  : pick(fmt_c, std::integral_constant<int, MODE_PAIR>{});
+  };
+  const int rc = fmt == A3D_DTYPE_F16 ? pick_mode(std::integral_constant<int, A3D_DTYPE_F16>{})
+                                      : pick_mode(std::integral_constant<int, A3D_DTYPE_BF16>{});
   if (rc == A3D_OK && launches) ++*launches;
   return rc;
 }

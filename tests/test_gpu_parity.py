@@ -283,14 +283,21 @@ def test_k_copies_of_one_latent_equal_single_decode(a3d_mod, decoders):
     assert np.array_equal(single, b['mean_prob'].cpu().numpy())
 
 
-@pytest.mark.parametrize('B,K,chunk', [(37, 1, 32), (33, 1, 32), (3, 2, 32), (1, 1, 32)])
-def test_pair_tail_matches_previous_tail_kernel(a3d_mod, weights, B, K, chunk, monkeypatch):
-    """K = 1 puts two consecutive OBJECTS into the two row slots of the pair tail (odd batches leave the second slot of the
-    last block of a chunk masked: 32 + 5 and 32 + 1 objects); the three-view kernel (A3D_TAIL_IMPL=v3, read when the handle is created) is the cross-check."""
+@pytest.mark.parametrize('impl', ['default', 'pair'])
+@pytest.mark.parametrize('B,K,chunk', [(37, 1, 32), (33, 1, 32), (3, 2, 32), (1, 1, 32), (2, 3, 32)])
+def test_tail_kernels_match_the_three_view_kernel(a3d_mod, weights, B, K, chunk, impl, monkeypatch):
+    """The default tail (one-sample blocks, whole h axis per tile, any K) and the pair tail (A3D_TAIL_IMPL=pair: two samples
+    per block for even K, two consecutive OBJECTS for K = 1 -- odd batches leave the second slot of the last block of a
+    chunk masked: 32 + 5 and 32 + 1 objects) against the three-view kernel (A3D_TAIL_IMPL=v3); the variable is read when
+    the handle is created."""
     ws = weights[('mn', 'trained')]
     rng = np.random.default_rng(100 + B)
     zc = rng.standard_normal((B, K, 64)).astype(np.float32)
     tgt = ar.make_targets(rng, B)
+    if impl == 'pair':
+        monkeypatch.setenv('A3D_TAIL_IMPL', 'pair')
+    else:
+        monkeypatch.delenv('A3D_TAIL_IMPL', raising=False)
     new = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=chunk)
     monkeypatch.setenv('A3D_TAIL_IMPL', 'v3')
     old = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=chunk)
