@@ -183,6 +183,25 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       const int blk = (int)(item % kItemsPerObj);
       const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
       const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
+      // this row's 2 x 2 x 2 outputs: od = 2 * d0 + pd, ...; an output is complete when the neighbour row on that side is
+      // inside the block (or the output itself lies outside the grid and is dropped).  The target bytes (one per (pd, ph):
+      // the pw = 0 / 1 outputs are adjacent bits) are fetched NOW so that their latency hides behind the K samples
+      const int64_t obj = K1 ? 2 * b + slot : b;
+      const bool fin = K1 ? obj < B : HCOL ? true : slot == 0;
+      const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
+      const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
+      const bool okd[2] = {ind && ld >= 1, ind && ld < kDLast};
+      const bool okh[2] = {inh && (HCOL || lh >= 1), inh && (HCOL || lh <= 6)};
+      const bool okw[2] = {inw && lw >= 1, inw && lw <= 2};
+      const int vbase = (2 * d0 * 64 + 2 * h0) * 64 + 2 * w0;
+      const int bit0 = (2 * w0) & 7;
+      uint32_t tbyte[4] = {0u, 0u, 0u, 0u};
+      if (target_bits && fin && (okw[0] || okw[1])) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (okd[q >> 1] && okh[q & 1])
+            tbyte[q] = target_bits[(size_t)obj * (A3D_VOXELS / 8) + ((vbase + (q >> 1) * 4096 + (q & 1) * 64) >> 3)];
+      }
       // running sums over the K samples, [pd][pw] as (ph = 0, ph = 1) pairs; with the sigmoid: sums of tanh(logit / 2)
       uint64_t psum[4];
 #pragma unroll
@@ -253,35 +272,19 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       }
       // ---- K >= 2: combine the two sample slots (rows r and r + 64 of a tile) through shared memory and finalize in
       //      slot 0;  K == 1: each slot finalizes its own object.  `slot` is uniform per warp.
-      const int64_t obj = K1 ? 2 * b + slot : b;
-      bool fin;
-      if constexpr (K1) {
-        fin = obj < B;
-      } else if constexpr (HCOL) {
-        fin = true;
-      } else {
+      if constexpr (MODE == MODE_PAIR) {
         uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
         if (slot == 1) {
 #pragma unroll
           for (int p = 0; p < 4; ++p) ex[p * kRows + r] = psum[p];
         }
         epi_sync();
-        fin = slot == 0;
         if (fin) {
 #pragma unroll
           for (int p = 0; p < 4; ++p) psum[p] = ptx::f2_add(psum[p], ex[p * kRows + r + 64]);
         }
       }
       if (fin) {
-        // this row's 2 x 2 x 2 outputs: od = 2 * d0 + pd, ...; an output is complete when the neighbour row on that side is
-        // inside the block (or the output itself lies outside the grid and is dropped)
-        const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
-        const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
-        const bool okd[2] = {ind && ld >= 1, ind && ld < kDLast};
-        const bool okh[2] = {inh && (HCOL || lh >= 1), inh && (HCOL || lh <= 6)};
-        const bool okw[2] = {inw && lw >= 1, inw && lw <= 2};
-        const int vbase = (2 * d0 * 64 + 2 * h0) * 64 + 2 * w0;
-        const int bit0 = (2 * w0) & 7;
         uint32_t packed = 0;   // tp | fp << 10 | fn << 20 (a warp adds at most 256 per field)
         float lsum = 0.f;
 #pragma unroll
@@ -290,7 +293,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           for (int ph = 0; ph < 2; ++ph) {
             if (!(okd[pd] && okh[ph] && (okw[0] || okw[1]))) continue;
             const int v0 = vbase + pd * 4096 + ph * 64;     // voxel index of the pw = 0 output; pw = 1 is the next bit
-            const uint32_t byte = target_bits ? target_bits[(size_t)obj * (A3D_VOXELS / 8) + (v0 >> 3)] : 0u;
+            const uint32_t byte = tbyte[pd * 2 + ph];
 #pragma unroll
             for (int pw = 0; pw < 2; ++pw) {
               if (!okw[pw]) continue;

@@ -1,0 +1,16 @@
+import sys, os, time
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch, a3d
+from a3d.presets import MODELNET_DECODER
+from oracle import decoder_ref as dr
+B = 256
+dec = a3d.decoder3D(MODELNET_DECODER, max_chunk=B)
+dec.set_weights(dr.keras_default_weights(MODELNET_DECODER, 1))
+z = torch.randn(B, 64, device='cuda')
+for _ in range(2): out = dec(z)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): out = dec(z)
+e1.record(); torch.cuda.synchronize()
+print('decoder(z) device in/out: %.3f ms per %d decodes = %.0f decodes/s' % (e0.elapsed_time(e1)/5, B, B*5/(e0.elapsed_time(e1)*1e-3)), type(out), getattr(out,'shape',None))
