@@ -385,9 +385,9 @@ def _main(args, saved_stdout):
                 'traffic': 30.17e9, 'traffic_unit': 'bytes per launch (ncu, profiles/r01_l4_ws2cta_ncu_full.txt)',
                 'peak_source': f'{src} sustained bf16', 'stage_ms': stage,
                 'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12,
-                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_pair_kernel (final ConvT + sigmoid + K-mean + threshold + counts)',
+                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_pair_kernel<MODE_HCOL> (final ConvT + sigmoid + K-mean + threshold + counts)',
                                'achieved': tail_gbs, 'peak': hpeak, 'unit': 'GB/s', 'frac': tail_gbs / hpeak,
-                               'traffic': 17.19e9,   # dram bytes of one launch, profiles/r01_tail_pair_ncu_full.txt
+                               'traffic': 17.28e9,   # dram bytes of one launch, profiles/r01_tail_hcol_ncu_full.txt
                                'algorithmic_bytes_per_launch': tail_bytes}}
 
     aux = None
