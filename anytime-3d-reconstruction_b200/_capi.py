@@ -92,6 +92,7 @@ SIGNATURES = {
     'a3d_enc2d_output_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     'a3d_enc2d_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     'a3d_enc2d_forward_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'a3d_enc2d_forward_host_u8': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]),
     'a3d_enc2d_split_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int,
                                          C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'a3d_enc2d_layer_shape': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),

@@ -69,6 +69,7 @@ struct a3d_enc2d {
   cudaStream_t hs_compute = nullptr, hs_copy = nullptr;
   cudaEvent_t hs_copied[2] = {nullptr, nullptr}, hs_consumed[2] = {nullptr, nullptr};
   float* hs_in[2] = {nullptr, nullptr};
+  uint8_t* hs_in_u8[2] = {nullptr, nullptr};   // a3d_enc2d_forward_host_u8: byte stages in front of hs_in
   float* hs_out = nullptr;
   int64_t hs_out_n = 0;
   bool no_p4 = false;         // A3D_ENC_P4=0: keep the shuffle pool in the resident-weight variant (cross-check)
@@ -417,6 +418,7 @@ void a3d_enc2d_destroy(a3d_enc2d* h) {
   for (auto& op : h->ops) { cudaFree(op.wgt); cudaFree(op.wgt_first16); cudaFree(op.scale); cudaFree(op.shift); }
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->hs_in[i]);
+    cudaFree(h->hs_in_u8[i]);
     if (h->hs_copied[i]) cudaEventDestroy(h->hs_copied[i]);
     if (h->hs_consumed[i]) cudaEventDestroy(h->hs_consumed[i]);
   }
@@ -487,7 +489,11 @@ int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n,
   return A3D_OK;
 }
 
-int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, float* out_dev_or_null, float* out_host_or_null) {
+namespace {
+// images_host: fp32 (u8_scale == 0) or uint8 bytes scaled by u8_scale on the device
+int forward_host_impl(a3d_enc2d* h, const void* images_host, float u8_scale, int64_t n, float* out_dev_or_null,
+                      float* out_host_or_null) {
+  const bool u8 = u8_scale != 0.f;
   int rc = check(h);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!images_host || (!out_dev_or_null && !out_host_or_null)))) {
@@ -508,6 +514,8 @@ int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, fl
       A3D_CUDA_OK(cudaMalloc(&h->hs_in[i], (size_t)mb * in_per * 4));
     }
   }
+  if (u8 && !h->hs_in_u8[0])
+    for (int i = 0; i < 2; ++i) A3D_CUDA_OK(cudaMalloc(&h->hs_in_u8[i], (size_t)mb * in_per));
   float* out_dev = out_dev_or_null;
   if (!out_dev) {
     if (n > h->hs_out_n) {
@@ -523,7 +531,10 @@ int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, fl
     const int b = (int)(c & 1);
     const int64_t off = c * mb, nc = n - off < mb ? n - off : mb;
     if (c >= 2) A3D_CUDA_OK(cudaStreamWaitEvent(h->hs_copy, h->hs_consumed[b], 0));   // stage b is free again
-    A3D_CUDA_OK(cudaMemcpyAsync(h->hs_in[b], images_host + off * in_per, (size_t)nc * in_per * 4, cudaMemcpyHostToDevice, h->hs_copy));
+    if (u8)
+      A3D_CUDA_OK(cudaMemcpyAsync(h->hs_in_u8[b], (const uint8_t*)images_host + off * in_per, (size_t)nc * in_per, cudaMemcpyHostToDevice, h->hs_copy));
+    else
+      A3D_CUDA_OK(cudaMemcpyAsync(h->hs_in[b], (const float*)images_host + off * in_per, (size_t)nc * in_per * 4, cudaMemcpyHostToDevice, h->hs_copy));
     A3D_CUDA_OK(cudaEventRecord(h->hs_copied[b], h->hs_copy));
     return A3D_OK;
   };
@@ -533,6 +544,7 @@ int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, fl
     const int64_t off = c * mb, nc = n - off < mb ? n - off : mb;
     if (c + 1 < chunks && (rc = copy_chunk(c + 1))) return sticky(h, rc);               // overlaps the forward of chunk c
     A3D_CUDA_OK(cudaStreamWaitEvent(h->hs_compute, h->hs_copied[b], 0));
+    if (u8 && (rc = sticky(h, launch_u8_to_f32(h->hs_in_u8[b], h->hs_in[b], (int64_t)nc * in_per, u8_scale, h->hs_compute, &h->launches)))) return rc;
     if ((rc = sticky(h, run_chunk(h, h->hs_in[b], A3D_IO_F32, nc, out_dev + off * out_per, A3D_IO_F32, h->hs_compute)))) return rc;
     A3D_CUDA_OK(cudaEventRecord(h->hs_consumed[b], h->hs_compute));
   }
@@ -545,6 +557,17 @@ int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, fl
     return A3D_ERR_CUDA;
   }
   return A3D_OK;
+}
+}  // namespace
+
+int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, float* out_dev_or_null, float* out_host_or_null) {
+  return forward_host_impl(h, images_host, 0.f, n, out_dev_or_null, out_host_or_null);
+}
+
+int a3d_enc2d_forward_host_u8(a3d_enc2d* h, const uint8_t* images_host, float scale, int64_t n, float* out_dev_or_null,
+                              float* out_host_or_null) {
+  if (!(scale > 0.f)) { set_error("a3d_enc2d_forward_host_u8: scale must be positive"); return A3D_ERR_INVALID; }
+  return forward_host_impl(h, images_host, scale, n, out_dev_or_null, out_host_or_null);
 }
 
 int a3d_enc2d_split_sample(a3d_enc2d* h, const float* enc_out_dev, int64_t n, int D, int out_stride, float clip,

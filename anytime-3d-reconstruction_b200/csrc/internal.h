@@ -128,6 +128,7 @@ int launch_global_pool(const float* in, float* out, int64_t n, int HW, int C, in
 // NHWC channel-(un)padding copies between user buffers (fp32 or 16-bit) and the 16-bit arena
 int launch_import_nhwc(const void* in, int in_is_f32, void* out, int64_t pixels, int C, int C_pad, int fmt,
                        cudaStream_t st, int64_t* launches);
+int launch_u8_to_f32(const uint8_t* in, float* out, int64_t total, float scale, cudaStream_t st, int64_t* launches);
 int launch_export_nhwc(const void* in, void* out, int out_is_f32, int64_t pixels, int C, int C_pad, int fmt,
                        cudaStream_t st, int64_t* launches);
 int launch_split_sample(const float* enc_out, int64_t n, int D, int out_stride, float clip, int seed_enable,

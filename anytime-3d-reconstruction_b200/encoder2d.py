@@ -71,6 +71,7 @@ class Encoder2D:
         self.operand_dtype = operand_dtype
         self._tdtype = torch.float16 if _capi.DTYPE[operand_dtype] == 0 else torch.bfloat16
         self.max_batch = int(max_batch)
+        self.uint8_scale = 1.0 / 255.0     # uint8 images are scaled like the loader does (pascal3D.py:242)
         d = _capi.Enc2dDesc()
         d.abi_version = _capi.A3D_ABI_VERSION
         d.in_h, d.in_w, d.in_ch = self.input_shape
@@ -185,7 +186,13 @@ class Encoder2D:
         torch = _torch()
         is_np = not isinstance(x, torch.Tensor)
         if is_np:
-            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            x = np.asarray(x)
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if x.dtype == np.uint8 else np.float32))
+        if x.dtype == torch.uint8:
+            # raw image bytes: the loader's `image / 255.` (pascal3D.py:242) runs on the device
+            if x.device.type == 'cpu' and out_dtype in ('fp32', 'f32', 'float32'):
+                return self._call_host(x.contiguous(), is_np)
+            x = x.to(self.device).to(torch.float32) * self.uint8_scale
         if x.device.type == 'cpu' and out_dtype in ('fp32', 'f32', 'float32'):
             return self._call_host(x.to(torch.float32).contiguous(), is_np)
         if x.dtype not in (torch.float32, self._tdtype) or self.input_shape[2] == 3:
@@ -207,7 +214,8 @@ class Encoder2D:
     predict = __call__
 
     def _call_host(self, x, is_np: bool):
-        """Host images (numpy / CPU tensor, pinned or pageable) through a3d_enc2d_forward_host: chunks of max_batch with
+        """Host images (numpy / CPU tensor, pinned or pageable; fp32, or uint8 bytes scaled by ``uint8_scale`` on the
+        device) through a3d_enc2d_forward_host[_u8]: chunks of max_batch with
         the H2D copy of chunk i+1 overlapping the forward of chunk i.  numpy in -> numpy out, CPU tensor in -> CUDA out."""
         torch = _torch()
         if tuple(x.shape[1:]) != self.input_shape:
@@ -222,8 +230,12 @@ class Encoder2D:
             out_dev, out_host = out.data_ptr(), None
         with torch.cuda.device(self.device_index):
             torch.cuda.current_stream().synchronize()      # the call runs on the handle's own streams
-            _capi.check(self._lib.a3d_enc2d_forward_host(self._h, x.data_ptr(), n, out_dev, out_host),
-                        'a3d_enc2d_forward_host')
+            if x.dtype == torch.uint8:
+                _capi.check(self._lib.a3d_enc2d_forward_host_u8(self._h, x.data_ptr(), self.uint8_scale, n, out_dev,
+                                                                out_host), 'a3d_enc2d_forward_host_u8')
+            else:
+                _capi.check(self._lib.a3d_enc2d_forward_host(self._h, x.data_ptr(), n, out_dev, out_host),
+                            'a3d_enc2d_forward_host')
         return out
 
     def split_sample(self, enc_out, D: int, seed: int | None = None, obj_offset: int = 0, clip: float = 10.0):
@@ -247,8 +259,10 @@ class Encoder2D:
     def encode(self, images, z_dim: int, seed: int | None = None, obj_offset: int = 0):
         """images -> (mean, logvar, z) CUDA tensors: forward + split_sample (the encoder half of getEval)."""
         torch = _torch()
-        x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images, np.float32))
-        return self.split_sample(self(x), z_dim, seed=seed, obj_offset=obj_offset)
+        if not isinstance(images, torch.Tensor):
+            images = np.asarray(images)
+            images = torch.from_numpy(np.ascontiguousarray(images, np.uint8 if images.dtype == np.uint8 else np.float32))
+        return self.split_sample(self(images), z_dim, seed=seed, obj_offset=obj_offset)
 
     # ---- diagnostics
     def debug_layer(self, layer: int, n: int) -> np.ndarray:

@@ -226,6 +226,19 @@ def config3_aux(a3d, dev, dtype, B=128, size=256, D16=16, steps=5):
     for i in range(steps):
         ce = step_host(i).cpu()
     e2e_s = (time.perf_counter() - t0) / steps
+    # the same step from the loader's raw bytes (uint8 NHWC, `image / 255.` of pascal3D.py:242 applied on the device):
+    # the H2D copy carries 25 MB instead of 100 MB per 128 crops (tests/tools/sweep_host_images.py: chunk-size sweep)
+    x_u8 = torch.from_numpy(np.clip(np.rint(x_host * 255.0), 0, 255).astype(np.uint8)).pin_memory()
+
+    def step_host_u8(i):   # one chunk of 128 on the resident handle: the 25 MB copy is shorter than a chunk's forward
+        _, _, z = enc.encode(x_u8, D16, seed=100 + i)
+        return a3d.anytime_eval(dec, z, ones, None, bits, K=1, seed=i, fill='normal')['counts']
+    step_host_u8(0).cpu()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step_host_u8(i).cpu()
+    e2e_u8_s = (time.perf_counter() - t0) / steps
     enc_h.close()
     alg, dense = er.encoder_macs(layers, size, size, 3)
     out = {'workload': f'Pascal3D multi-modal image encoder (Darknet19 + head2D, {size}x{size} RGB) + voxel decoder '
@@ -235,6 +248,8 @@ def config3_aux(a3d, dev, dtype, B=128, size=256, D16=16, steps=5):
            'encoder_tflops_algorithmic': 2.0 * alg * B / (ms_enc * 1e-3) / 1e12,
            'encoder_macs_per_image': {'algorithmic': alg, 'dense': dense},
            'e2e': {'value': B / e2e_s, 'unit': 'objects/s', 'h2d_bytes_per_step': int(x_host.nbytes), 'd2h_bytes_per_step': B * 24},
+           'e2e_uint8_images': {'value': B / e2e_u8_s, 'unit': 'objects/s', 'h2d_bytes_per_step': int(x_u8.numel()),
+                                'd2h_bytes_per_step': B * 24},
            'gpu_launches_per_step': None, 'counts_tp_fp_fn': [int(v) for v in c.sum(0).tolist()]}
     l0 = enc.launch_count + dec.launch_count
     step(x, 0)

@@ -204,6 +204,12 @@ int a3d_enc2d_forward(a3d_enc2d* h, const void* in_dev, int in_dtype, int64_t n,
  * result ([n, h*w*c] fp32) goes to out_dev (device pointer) and / or out_host; synchronous. */
 int a3d_enc2d_forward_host(a3d_enc2d* h, const float* images_host, int64_t n, float* out_dev_or_null, float* out_host_or_null);
 
+/* Same call with the loader's raw bytes: uint8 NHWC images, multiplied by `scale` on the device (the reference's loader
+ * does `image = image / 255.` on the host before the model sees it, src/dataset_loader/pascal3D.py:242; pass 1/255).
+ * The H2D copy carries one byte per sample instead of four: the host path of a 256 x 256 batch is PCIe bound. */
+int a3d_enc2d_forward_host_u8(a3d_enc2d* h, const uint8_t* images_host, float scale, int64_t n, float* out_dev_or_null,
+                              float* out_host_or_null);
+
 /* Latent split of the callers + sampling()  src/module/nolbo.py:869-875; src/module/function.py:35-38:
  * mean = enc_out[:, :D]; logvar = clip(enc_out[:, D:2D], -clip, clip); z = mean + sqrt(exp(logvar)) * eps,
  * eps ~ N(0,1) from Philox4x32-10 with counter (dim/4, 0x5A4D504C, obj_offset + b), key = seed (eps = 0 if

@@ -293,3 +293,27 @@ def test_host_image_path_matches_device_path(a3d_mod):
     assert pinned.is_cuda and np.array_equal(pinned.cpu().numpy(), dev)
     assert enc(np.zeros((0, 64, 64, 3), np.float32)).shape == (0, 32)
     enc.close()
+
+
+def test_uint8_image_bytes_match_the_scaled_float_images(a3d_mod):
+    """a3d_enc2d_forward_host_u8: raw image bytes, `image / 255.` (pascal3D.py:242) applied on the device.  The device
+    multiplies by fl(1/255) where numpy divides by 255: at most one ulp apart before the 16-bit rounding of the image
+    layer's operands, so the outputs agree to operand precision; two calls on the same bytes are bit-identical."""
+    layers = er.layer_list()
+    ws = er.keras_default_weights(layers, 3, seed=31)
+    enc = a3d_mod.image_encoder(a3d_mod.presets.PASCAL_ENCODER_HEAD, input_size=(64, 64), max_batch=3)
+    enc.set_weights(ws)
+    u8 = np.random.default_rng(5).integers(0, 256, (8, 64, 64, 3), dtype=np.uint8)     # chunks of 3 / 3 / 2
+    ref = enc((u8.astype(np.float32) / 255.).astype(np.float32))
+    got = enc(u8)                                            # numpy uint8 -> numpy through the byte pipeline
+    assert isinstance(got, np.ndarray) and got.shape == ref.shape and np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 2e-3 * max(1.0, float(np.abs(ref).max()))
+    assert np.array_equal(enc(u8), got)
+    pinned = enc(torch.from_numpy(u8).pin_memory())          # pinned CPU bytes -> CUDA tensor
+    assert pinned.is_cuda and np.array_equal(pinned.cpu().numpy(), got)
+    dev = enc(torch.from_numpy(u8).cuda())                   # device-resident bytes: scaled by torch, same model call
+    assert np.abs(dev.cpu().numpy() - ref).max() <= 2e-3 * max(1.0, float(np.abs(ref).max()))
+    mean, logvar, z = enc.encode(u8, 16, seed=3)
+    assert tuple(z.shape) == (8, 16) and torch.isfinite(z).all()
+    enc.close()
+
