@@ -53,8 +53,9 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
 __device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory"); }
 
-// SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 = sigmoid as
-// 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities or the BCE loss are emitted)
+// SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 / 3 = sigmoid
+// as 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities (2) or the BCE loss (3) are
+// emitted; the loss code is compiled out of 2)
 // MODE_PAIR1: K == 1 -- the two row slots hold two CONSECUTIVE OBJECTS (2j, 2j + 1) instead of two samples of one object;
 // no slot combine and no block-wide barrier, every slot finalizes its own object.
 template <int FMT, int SIG, int MODE>
@@ -259,7 +260,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             ptx::f2_unpack(ptx::f2_mul(o1, half2), b0, b1);
             o0 = ptx::f2_pack(ptx::tanh_approx(a0), ptx::tanh_approx(a1));
             o1 = ptx::f2_pack(ptx::tanh_approx(b0), ptx::tanh_approx(b1));
-          } else if constexpr (SIG == 2) {
+          } else if constexpr (SIG >= 2) {
             float a0, a1, b0, b1;
             ptx::f2_unpack(o0, a0, a1);
             ptx::f2_unpack(o1, b0, b1);
@@ -320,6 +321,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             if (!(okd[pd] && okh[ph] && (okw[0] || okw[1]))) continue;
             const int v0 = vbase + pd * 4096 + ph * 64;     // voxel index of the pw = 0 output; pw = 1 is the next bit
             const uint32_t byte = tbyte[pd * 2 + ph];
+            float mpair = 0.f;
 #pragma unroll
             for (int pw = 0; pw < 2; ++pw) {
               if (!okw[pw]) continue;
@@ -327,12 +329,19 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
               ptx::f2_unpack(psum[pd * 2 + pw], v2[0], v2[1]);
               // mean of sigmoid = 0.5 + 0.5 * mean of tanh(logit / 2)
               const float mval = SIG == 1 ? fmaf(v2[ph], 0.5f * invk, 0.5f) : v2[ph] * invk;
-              if (mean_prob) mean_prob[(size_t)obj * A3D_VOXELS + v0 + pw] = mval;
+              if (mean_prob) {   // the pw = 0 / 1 outputs are adjacent floats: one 8-byte store when both are complete
+                if (okw[0] && okw[1]) {
+                  if (pw == 0) mpair = mval;
+                  else *reinterpret_cast<float2*>(mean_prob + (size_t)obj * A3D_VOXELS + v0) = make_float2(mpair, mval);
+                } else {
+                  mean_prob[(size_t)obj * A3D_VOXELS + v0 + pw] = mval;
+                }
+              }
               if (target_bits) {
                 const uint32_t t = (byte >> (bit0 + pw)) & 1u;
                 const uint32_t yv = mval >= thr;
                 packed += (t & yv) + (((t ^ 1u) & yv) << 10) + ((t & (yv ^ 1u)) << 20);
-                if (loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
+                if (SIG != 2 && loss) {   // weighted BCE, function.py:73-82: clip to [1e-7, 1 - 1e-7] in fp32 like tf.clip_by_value
                   const float pc = fminf(fmaxf(mval, 1e-7f), 1.f - 1e-7f);
                   lsum -= t ? gamma * logf(pc) : (1.f - gamma) * logf(1.f - pc);
                 }
@@ -340,7 +349,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             }
           }
         if (target_bits) {
-          if (loss) {
+          if (SIG != 2 && loss) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
             if (lane == 0 && lsum != 0.f) atomicAdd(loss + obj, (double)lsum);
@@ -379,12 +388,13 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
     return A3D_OK;
   };
   // sigmoid mode: 1 = tanh form for the counts-only path, 2 = exp form whenever probabilities or the loss are emitted
-  const int sig = !final_sigmoid ? 0 : (mean_prob || loss) ? 2 : 1;
+  const int sig = !final_sigmoid ? 0 : loss ? 3 : mean_prob ? 2 : 1;
   auto pick = [&](auto fmt_c, auto mode_c) -> int {
     constexpr int F = decltype(fmt_c)::value;
     constexpr int M = decltype(mode_c)::value;
     return sig == 0 ? launch(tail_pair_kernel<F, 0, M>)
-                    : sig == 1 ? launch(tail_pair_kernel<F, 1, M>) : launch(tail_pair_kernel<F, 2, M>);
+                    : sig == 1 ? launch(tail_pair_kernel<F, 1, M>)
+                               : sig == 2 ? launch(tail_pair_kernel<F, 2, M>) : launch(tail_pair_kernel<F, 3, M>);
   };
   auto pick_mode = [&](auto fmt_c) -> int {
     return mode == MODE_HCOL ? pick(fmt_c, std::integral_constant<int, MODE_HCOL>{})
