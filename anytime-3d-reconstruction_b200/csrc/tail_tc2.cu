@@ -1,23 +1,27 @@
-// Fused tail, "pair" variant (default for even K): same maths as tail_tc.cu --
+// Fused tail (default kernel, three block shapes) -- same maths as tail_tc.cu:
 //   final Conv3DTranspose(64 -> 1, k4, s2, 'same', no bias, no BN) + tf.sigmoid   autoencoder3D.py:129-136
 //   mean over the K post-sigmoid grids of an object                                 nolbo_test.py:167-177
 //   yPred = (mean >= thr), TP / FP / FN (+ weighted BCE) against the bit-packed target   function.py:100-115,73-82
-// -- with 1.75x less shared-memory operand traffic per block, which is what bounds this kernel (tail_tc.cu reads every
-// activation tile three times through w-shifted descriptor views with N = 32 MMAs).
+// with every activation tile read ONCE by the tensor core (tail_tc.cu reads it three times through w-shifted descriptor
+// views with N = 32 MMAs).
 //
-// A CTA block is 4 (w) x 8 (d) x 8 (h) input voxels of TWO consecutive samples of one object; GEMM rows are ordered
-// (w, sample, d, h), so M-tile m (128 rows) is exactly w-slice m of both samples.  ONE MMA per (tile, K step) with N = 64:
+// A CTA block is four w-slices of 128 GEMM rows; M-tile m is exactly w-slice m.  The rows of a tile are
+//   MODE_HCOL (default, any K):  (d 4, h 32) of ONE sample -- a warp is one d line with the whole h axis, no h halo;
+//   MODE_PAIR / MODE_PAIR1:      (sample 2, d 8, h 8) -- two samples of one object (even K) or two consecutive objects (K = 1).
+// ONE MMA per (tile, K step) with N = 64:
 //   columns  0..15  Za0[(td, j)]  = X . W[td, th(j), tap_w = 1]        (delta_w = 0, output parity pw = 0)
 //   columns 16..31  Za1[(td, j)]  = X . W[td, th(j), tap_w = 2]        (delta_w = 0, output parity pw = 1)
 //   columns 32..47  Zm[(td, j)]   = X . W[td, th(j), tap_w = 3]        (feeds output parity pw = 0 of slice m + 1)
 //   columns 48..63  Zp[(td, j)]   = X . W[td, th(j), tap_w = 0]        (feeds output parity pw = 1 of slice m - 1)
 // with th(j) = (j + 1) & 3, i.e. the h taps in the order 1, 2, 3, 0: (th 1, th 2) are the delta_h = 0 taps of output
 // parities ph = 0 / 1 and (th 3, th 0) their delta_h = -1 / +1 partners, so every epilogue add works on an aligned
-// register PAIR and is issued as one packed add.rn.f32x2 (FADD2): the epilogue is issue-bound, not FLOP-bound.
+// register PAIR and is issued as one packed add.rn.f32x2 (FADD2).
 // The w-axis col2im is then free: the accumulators of slices m - 1, m, m + 1 live in the SAME TMEM lanes, in different
 // column blocks, so the epilogue thread of (slice m, row r) simply loads Za from block m, Zm from block m - 1 and Zp
-// from block m + 1.  h axis by warp shuffles, d axis by one shared-memory exchange, as in tail_tc.cu.  Blocks advance by
-// 3 slices in w (6 complete output columns) and by 7 voxels in d and h (14 complete outputs).
+// from block m + 1.  h axis by warp shuffles, d axis by one shared-memory exchange.  Blocks advance by 3 slices in w
+// (6 complete output columns) and by 3 (HCOL) or 7 (PAIR) voxels in d / 7 in h (PAIR).
+// What bounds the kernel is the activation bytes that cross the L2 -> SM fabric (halo rows) and the shared-memory port
+// (TMA writes + operand reads + exchange); see profiles/r01_notes.md for the ablations.
 #include <cstdlib>
 #include <type_traits>
 
