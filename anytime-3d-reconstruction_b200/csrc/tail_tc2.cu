@@ -315,6 +315,45 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
           }
         }
+      } else if constexpr (SIG == 2) {
+        // probabilities (and optionally counts), no loss: decoder(z) and return_grid.  Same bit order p as above.
+        if (fin) {
+          float mv[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {            // q = pd * 2 + pw holds (ph = 0, ph = 1)
+            float v0, v1;
+            ptx::f2_unpack(psum[q], v0, v1);
+            const int pd = q >> 1, pw = q & 1;
+            mv[(pd * 2 + 0) * 2 + pw] = v0 * invk;
+            mv[(pd * 2 + 1) * 2 + pw] = v1 * invk;
+          }
+          if (mean_prob) {
+            float* base = mean_prob + (size_t)obj * A3D_VOXELS + vbase;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // q = pd * 2 + ph; the pw = 0 / 1 outputs are adjacent floats
+              if (!(okd[q >> 1] && okh[q & 1])) continue;
+              float* dst = base + (q >> 1) * 4096 + (q & 1) * 64;
+              if (okw[0] && okw[1]) *reinterpret_cast<float2*>(dst) = make_float2(mv[2 * q], mv[2 * q + 1]);
+              else if (okw[0]) dst[0] = mv[2 * q];
+              else if (okw[1]) dst[1] = mv[2 * q + 1];
+            }
+          }
+          if (target_bits) {
+            uint32_t Y = 0u, T = 0u;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) Y |= (uint32_t)(mv[p] >= thr) << p;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) T |= ((tbyte[q] >> bit0) & 3u) << (2 * q);
+            const uint32_t M = ((okd[0] ? 0x0Fu : 0u) | (okd[1] ? 0xF0u : 0u)) & ((okh[0] ? 0x33u : 0u) | (okh[1] ? 0xCCu : 0u)) &
+                               ((okw[0] ? 0x55u : 0u) | (okw[1] ? 0xAAu : 0u));
+            uint32_t packed = __popc(Y & T & M) | (__popc(Y & ~T & M) << 10) | (__popc(~Y & T & M) << 20);
+            packed = __reduce_add_sync(0xffffffffu, packed);
+            if (lane < 3) {
+              const uint32_t f = (packed >> (10 * lane)) & 1023u;
+              if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
+            }
+          }
+        }
       } else if (fin) {
         uint32_t packed = 0;   // tp | fp << 10 | fn << 20 (a warp adds at most 256 per field)
         float lsum = 0.f;
