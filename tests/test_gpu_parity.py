@@ -317,6 +317,35 @@ def test_tail_kernels_match_the_three_view_kernel(a3d_mod, weights, B, K, chunk,
     assert torch.equal(a['counts'][:, 0] + a['counts'][:, 1], (mp >= 0.5).sum(1))
 
 
+def test_decode_and_eval_are_cuda_graph_capturable(a3d_mod, decoders):
+    """every hot call is asynchronous on the caller's stream with no hidden synchronisation or
+    allocation, so a decode (and a fused anytime evaluation) can be captured into a CUDA graph and replayed on new
+    latents; the replay equals the eager call bit for bit."""
+    dec = decoders[('mn', 'trained')]
+    g0 = torch.Generator(device='cuda').manual_seed(5)
+    z1 = torch.randn(8, 64, device='cuda', generator=g0)
+    z2 = torch.randn(8, 64, device='cuda', generator=g0)
+    tgt = ar.pack_bits(ar.make_targets(np.random.default_rng(3), 2))
+    bits = torch.from_numpy(tgt).cuda()
+    zin = z1.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up off the default stream, as torch asks before a capture
+        dec(zin)
+        a3d_mod.anytime_eval(dec, None, None, None, bits, z_completed=zin.view(2, 4, 64))
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = dec(zin)
+        cnt = a3d_mod.anytime_eval(dec, None, None, None, bits, z_completed=zin.view(2, 4, 64))['counts']
+    for z in (z2, z1):
+        zin.copy_(z)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, dec(z))
+        assert torch.equal(cnt, a3d_mod.anytime_eval(dec, None, None, None, bits, z_completed=z.view(2, 4, 64))['counts'])
+
+
 def test_getEval_reference_return_tuple(a3d_mod, decoders):
     dec = decoders[('mn', 'trained')]
     rng = np.random.default_rng(8)
