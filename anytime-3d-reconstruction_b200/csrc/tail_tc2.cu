@@ -120,8 +120,8 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     __syncwarp();
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int64_t b = item / kItemsPerObj;
-      const int blk = (int)(item % kItemsPerObj);
+      const int b = (int)item / kItemsPerObj;    // the launcher guarantees total_items < 2^31: 32-bit division by a constant
+      const int blk = (int)item - b * kItemsPerObj;
       const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
       const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
       for (int kp = 0; kp < pairs; ++kp, ++it) {
@@ -130,7 +130,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&a_full[s], kABytes);
           // tensor-map dims are (c, h, d, n, w): rows land as (w, sample, d, h) with h fastest (HCOL: box 64 x 32 x 4 x 1 x 4)
-          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, (int)(K1 ? 2 * b : HCOL ? b * K + kp : b * K + 2 * kp), aw);
+          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, K1 ? 2 * b : HCOL ? b * K + kp : b * K + 2 * kp, aw);
         }
         __syncwarp();
       }
@@ -184,14 +184,14 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     uint64_t* exq = reinterpret_cast<uint64_t*>(exD);   // exchange buffers as (ph = 0, ph = 1) pairs: [2][4][kRows]
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int64_t b = item / kItemsPerObj;
-      const int blk = (int)(item % kItemsPerObj);
+      const int b = (int)item / kItemsPerObj;    // the launcher guarantees total_items < 2^31: 32-bit division by a constant
+      const int blk = (int)item - b * kItemsPerObj;
       const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
       const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
       // this row's 2 x 2 x 2 outputs: od = 2 * d0 + pd, ...; an output is complete when the neighbour row on that side is
       // inside the block (or the output itself lies outside the grid and is dropped).  The target bytes (one per (pd, ph):
       // the pw = 0 / 1 outputs are adjacent bits) are fetched NOW so that their latency hides behind the K samples
-      const int64_t obj = K1 ? 2 * b + slot : b;
+      const int64_t obj = K1 ? 2 * (int64_t)b + slot : b;
       const bool fin = K1 ? obj < B : HCOL ? true : slot == 0;
       const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
       const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
@@ -423,6 +423,7 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
   if (!hcol && K != 1 && (K & 1)) { set_error("tail_pair: K must be 1 or even"); return A3D_ERR_INVALID; }
   const int mode = hcol ? MODE_HCOL : K == 1 ? MODE_PAIR1 : MODE_PAIR;
   const int64_t items = mode == MODE_HCOL ? B * kItemsHcol : (mode == MODE_PAIR1 ? (B + 1) / 2 : B) * kItemsPair;
+  if (items > 0x7fffffffll || B * (int64_t)K > 0x7fffffffll) { set_error("tail: batch too large for one launch"); return A3D_ERR_INVALID; }
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
