@@ -402,7 +402,7 @@ def _main(args, saved_stdout):
                 'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12,
                 'fused_tail': {'bound': 'hbm', 'kernel': 'tail_pair_kernel<MODE_HCOL> (final ConvT + sigmoid + K-mean + threshold + counts)',
                                'achieved': tail_gbs, 'peak': hpeak, 'unit': 'GB/s', 'frac': tail_gbs / hpeak,
-                               'traffic': 17.28e9,   # dram bytes of one launch, profiles/r01_tail_hcol_ncu_full.txt
+                               'traffic': 17.20e9,   # dram bytes of one launch, profiles/r01_tail_hcol_final_ncu_full.txt
                                'algorithmic_bytes_per_launch': tail_bytes}}
 
     aux = None
