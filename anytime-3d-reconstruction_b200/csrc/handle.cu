@@ -116,8 +116,9 @@ struct a3d_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
   int sticky = 0;
-  bool l4_generic = false;   // A3D_L4_IMPL=generic: run the 128->64 layer on the generic 1-CTA kernel instead of the
-                             // 2-CTA weight-stationary one (parity-identical, ~15 % slower: shared-memory-bandwidth bound)
+  int l4_impl = 0;           // 128->64 layer: 0 = w-sweep 2-CTA kernel (convt_l4_sw.cu, default); A3D_L4_IMPL=ws: the
+                             // round-1 h-sweep kernel (convt_l4_ws.cu); A3D_L4_IMPL=generic: the 1-CTA kernel of the other
+                             // stride-2 layers (cross-checks; all three are parity-identical up to summation order)
 };
 
 namespace {
@@ -203,6 +204,31 @@ void pack_ws_weights(const std::vector<float>& wk, int cin, int cout, int fmt, s
               if (r < 64) { tw = rank == 0 ? 1 : 2; co = r; }            // dw = 0: rank 0 = pw0, rank 1 = pw1
               else if (r < 96) { tw = 3; co = 32 * rank + (r - 64); }     // dw = -1 (pw0), N-half of this rank
               else { tw = 0; co = 32 * rank + (r - 96); }                 // dw = +1 (pw1), N-half of this rank
+              const size_t tap = ((size_t)td * 4 + th) * 4 + tw;
+              const float* src = &wk[(tap * cout + co) * cin + (size_t)c * 64];
+              uint16_t* dst = &out[row * 64];
+              for (int i = 0; i < 64; ++i) dst[i] = cvt16(src[i], fmt);
+            }
+        }
+  }
+}
+
+// w-sweep 2-CTA layout of the 128->64 layer (convt_l4_sw.cu): [class q = pd*2+ph][rank][sd][sh][chunk][128 rows];
+// rank 0 holds the w taps 0 and 1, rank 1 the taps 2 and 3 (64 output channels each): the N = 256 B operand of a K step
+// is [tap0 | tap1 | tap2 | tap3], i.e. the accumulator blocks (j-1, pw 1), (j, pw 0), (j, pw 1), (j+1, pw 0).
+void pack_sw_weights(const std::vector<float>& wk, int cin, int cout, int fmt, std::vector<uint16_t>& out) {
+  const int chunks = cin / 64;
+  out.resize((size_t)4 * 2 * 4 * chunks * 128 * 64);
+  size_t row = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int pd = q >> 1, ph = q & 1;
+    for (int rank = 0; rank < 2; ++rank)
+      for (int sd = 0; sd < 2; ++sd)
+        for (int sh = 0; sh < 2; ++sh) {
+          const int td = tap_of(pd, sd), th = tap_of(ph, sh);
+          for (int c = 0; c < chunks; ++c)
+            for (int r = 0; r < 128; ++r, ++row) {
+              const int tw = 2 * rank + (r >> 6), co = r & 63;
               const size_t tap = ((size_t)td * 4 + th) * 4 + tw;
               const float* src = &wk[(tap * cout + co) * cin + (size_t)c * 64];
               uint16_t* dst = &out[row * 64];
@@ -330,6 +356,19 @@ int finalize_weights(a3d_handle* h) {
       CUresult r = enc(&L.tmap_wgt_ws, dt, 2, L.wgt_ws, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(ws weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+      pack_sw_weights(h->w[base], L.cin, L.cout, fmt, p16);
+      if ((rc = upload(p16.data(), p16.size() * 2, &L.wgt_sw))) return rc;
+      r = enc(&L.tmap_wgt_sw, dt, 2, L.wgt_sw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sw weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+      const uint64_t W = L.win, C = L.cin;
+      cuuint64_t ad[5] = {C, (cuuint64_t)h->max_chunk, W, W, W};   // (c, n, h, w, d)
+      cuuint64_t as[4] = {W * W * W * C * 2, W * C * 2, C * 2, W * W * C * 2};
+      cuuint32_t ab[5] = {64, 8, (cuuint32_t)(L.win + 2), 1, 1};
+      cuuint32_t ae[5] = {1, 1, 1, 1, 1};
+      r = enc(&L.tmap_act_sw, dt, 5, h->act[li + 1], ad, as, ab, ae, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sw activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
     }
   }
   // final kernel [4,4,4,1,64] is already [tap][ci]
@@ -423,7 +462,10 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
   for (int li = 0; li < 3; ++li) {
     if (h->desc.impl == A3D_IMPL_SIMT)
       rc = launch_convt_s2_simt(h->conv[li], h->act[li + 1], h->act[li + 2], n, fmt, act, st, &h->launches);
-    else if (li == 2 && !h->l4_generic)
+    else if (li == 2 && h->l4_impl == 0)
+      rc = launch_convt_l4_sw(h->conv[li].tmap_act_sw, h->conv[li].tmap_wgt_sw, h->act[li + 2], h->conv[li].scale,
+                              h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
+    else if (li == 2 && h->l4_impl == 1)
       rc = launch_convt_l4_ws(h->conv[li].tmap_act, h->conv[li].tmap_wgt_ws, h->act[li + 2], h->conv[li].scale,
                               h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
     else
@@ -541,7 +583,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   h->dense_units = h->grid0 * h->grid0 * h->grid0 * h->ch0;  // :120
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
-  { const char* e = getenv("A3D_L4_IMPL"); h->l4_generic = e && std::string(e) == "generic"; }
+  { const char* e = getenv("A3D_L4_IMPL"); h->l4_impl = !e ? 0 : std::string(e) == "generic" ? 2 : std::string(e) == "ws" ? 1 : 0; }
   { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; h->tail_pair = e && std::string(e) == "pair"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
@@ -570,7 +612,7 @@ void a3d_destroy(a3d_handle* h) {
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
   cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16); cudaFree(h->d_w5_pair);
-  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
+  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_sw); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

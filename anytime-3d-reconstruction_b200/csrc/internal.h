@@ -42,8 +42,11 @@ struct ConvLayer {
   CUtensorMap tmap_wgt;   // 2-D view (64 ci, rows) of the per-(parity,tap,chunk) repacked weights, box (64, 256), SW128
   CUtensorMap tmap_wgt64; // same tensor, box (64, 64): N-half loads of the 2-CTA path
   void* wgt_packed = nullptr;   // device, 16-bit
-  CUtensorMap tmap_wgt_ws;      // weight-stationary 2-CTA layout (128->64 layer only)
+  CUtensorMap tmap_wgt_ws;      // weight-stationary 2-CTA layout (128->64 layer only, convt_l4_ws.cu)
   void* wgt_ws = nullptr;
+  CUtensorMap tmap_act_sw;      // w-sweep kernel (convt_l4_sw.cu): (c, n, h, w, d) view, box (64, 8, W+2, 1, 1)
+  CUtensorMap tmap_wgt_sw;      // ... its resident weights: [class][rank][sd][sh][chunk][2 taps x 64 co] rows
+  void* wgt_sw = nullptr;
   // SIMT path: [tap 64][ci][co] 16-bit
   void* wgt_tco = nullptr;
   float* scale = nullptr;  // folded BN: y = scale*conv + shift
@@ -60,6 +63,9 @@ int launch_gemm_l1(const CUtensorMap& tmap_a0, const CUtensorMap& tmap_mt, void*
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
 int launch_convt_l4_ws(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
+                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
+                       cudaStream_t st, int64_t* launches);
+int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
                        const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
 int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t n, int fmt, int act,

@@ -2,7 +2,7 @@
 
 # test_modelnet_VAE_dr.py:176-185 (latent dim 64)
 MODELNET_DECODER = {
-    'name': 'docoder',
+    'name': 'decoder',
     'input_dim': 64,
     'output_shape': [64, 64, 64, 1],
     'filter_num_list': [512, 256, 128, 64, 1],

@@ -31,7 +31,7 @@ BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
 
 # ModelNet decoder structure, test_modelnet_VAE_dr.py:176-185 of the reference
 MODELNET_DECODER = {
-    'name': 'docoder',
+    'name': 'decoder',
     'input_dim': 64,
     'output_shape': [64, 64, 64, 1],
     'filter_num_list': [512, 256, 128, 64, 1],
@@ -173,11 +173,13 @@ def decoder_forward(structure: dict, weights: list, z, dtype=torch.float32, retu
 
 
 def trained_like_weights(structure: dict, seed: int, calib: int = 4, logit_std: float = 3.0,
-                         logit_mean: float = -3.3) -> list[np.ndarray]:
+                         logit_mean: float = -3.3, bf16_kernels: bool = True) -> list[np.ndarray]:
     """Deterministic "trained-like" weights: Glorot kernels, BN moving statistics calibrated on random
     latents (so every hidden layer is ~N(0,1) before ELU with randomised gamma/beta), and a final kernel
     scaled/offset so logits have std ~= ``logit_std`` and mean ~= ``logit_mean`` (occupancy ~ 10-15 %).
     Kernels are rounded to bf16-representable values; BN vectors stay fp32 (applied in fp32 on both sides).
+    ``bf16_kernels=False`` keeps full fp32 kernels, i.e. what a trained reference checkpoint holds (the GPU then sees
+    the 16-bit rounding of the operands while the oracle computes with the fp32 originals).
     """
     rng = np.random.Generator(np.random.PCG64(seed + 7919))
     ws = keras_default_weights(structure, seed, bf16_kernels=False)
@@ -192,7 +194,7 @@ def trained_like_weights(structure: dict, seed: int, calib: int = 4, logit_std: 
             ws[i] = (0.25 * rng.standard_normal(ws[i].shape)).astype(np.float32)
         elif n == 'dense/bias':
             ws[i] = (0.05 * rng.standard_normal(ws[i].shape)).astype(np.float32)
-        elif n.endswith('/kernel'):
+        elif n.endswith('/kernel') and bf16_kernels:
             ws[i] = round_bf16(ws[i])
     bn_layers = [i for i, n in enumerate(names) if n.endswith('/moving_mean')]
     for li, mi in enumerate(bn_layers):
@@ -236,5 +238,7 @@ def trained_like_weights(structure: dict, seed: int, calib: int = 4, logit_std: 
     tot = a * l0 + b * s0
     a *= logit_std / float(tot.std())
     b = (logit_mean - a * float(l0.mean())) / float(s0.mean())
-    ws[k5] = round_bf16((a * base + b).astype(np.float32))
+    ws[k5] = (a * base + b).astype(np.float32)
+    if bf16_kernels:
+        ws[k5] = round_bf16(ws[k5])
     return ws

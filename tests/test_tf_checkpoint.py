@@ -101,7 +101,7 @@ def test_keras_order_is_numeric_by_layer_then_variable(tmp_path):
     bn = ['gamma', 'beta', 'moving_mean', 'moving_variance']
     names = [['kernel', 'bias'], bn] + sum([[['kernel'], bn] for _ in range(4)], []) + [['kernel']]
     assert sum(len(n) for n in names) == 27
-    prefix = str(tmp_path / 'docoder')
+    prefix = str(tmp_path / 'decoder')
     tc.save_keras_weights(prefix, ws, names)
     assert tc.is_checkpoint(prefix)
     back = tc.load_keras_weights(prefix)
