@@ -27,12 +27,13 @@ import os
 import numpy as np
 
 from . import _capi, presets
-from ._capi import FILL, VOXELS
+from ._capi import FILL, OUT, VOXELS
 from .encoder2d import Darknet19, Encoder2D, head2D, image_encoder
 from .encoder3d import Encoder3D, encoder3D
 
 __all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'voxelPrecisionRecallSweep', 'binary_loss',
            'anytime_eval', 'anytime_eval_host', 'impute', 'getEval', 'pack_targets', 'iou_from_counts', 'shard_range',
+           'nearest_prior', 'pinned_empty',
            'allreduce_counts', 'Darknet19', 'head2D', 'image_encoder', 'Encoder2D', 'getEvalImages', 'encoder3D', 'Encoder3D', 'getEvalVoxels']
 
 
@@ -204,22 +205,46 @@ class Decoder3D:
             self.set_weights([f[f'arr_{i}'] for i in range(len(f.files))])
 
     # ---- forward
-    def __call__(self, latents, training: bool = False):
-        """decoder(z, training=False) -> [B, 64, 64, 64, 1] float32 (NDHWC).  numpy in -> numpy out;
-        torch in -> CUDA torch tensor out."""
+    def __call__(self, latents, training: bool = False, out=None, out_dtype: str = 'f32', threshold: float = 0.5):
+        """decoder(z, training=False) -> [B, 64, 64, 64, 1] float32 (NDHWC).  numpy in -> numpy out (through the
+        host-buffer entry a3d_decode_host: device->host copies overlapped with the decode); torch in -> CUDA torch
+        tensor out (a3d_decode on the current stream).
+
+        Extras for the numpy path (not in the reference): ``out`` = a preallocated result array, ideally from
+        ``a3d.pinned_empty`` (page-locked memory: the copy then runs at the PCIe rate; a fresh pageable array is
+        allocated otherwise); ``out_dtype`` = 'f32' (the Keras output), 'f16' (half the bytes) or 'bits'
+        ([B, 32768] uint8, bit = p >= threshold, packed like the targets)."""
         if training:
             raise NotImplementedError('a3d implements the inference path only (training=False)')
         torch = _torch()
-        is_np = not isinstance(latents, torch.Tensor)
+        if not isinstance(latents, torch.Tensor):
+            return self.decode_host(latents, out=out, out_dtype=out_dtype, threshold=threshold)
         z = _as_dev_f32(latents, torch, self.device).reshape(-1, self.input_dim)
         n = z.shape[0]
-        out = torch.empty((n, 64, 64, 64, 1), dtype=torch.float32, device=self.device)
+        res = torch.empty((n, 64, 64, 64, 1), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device_index):
-            _capi.check(self._lib.a3d_decode(self._h, z.data_ptr(), n, out.data_ptr(), _stream_ptr(torch)),
+            _capi.check(self._lib.a3d_decode(self._h, z.data_ptr(), n, res.data_ptr(), _stream_ptr(torch)),
                         'a3d_decode')
-        return out.cpu().numpy() if is_np else out
+        return res
 
     predict = __call__
+
+    def decode_host(self, latents, out=None, out_dtype: str = 'f32', threshold: float = 0.5) -> np.ndarray:
+        """numpy latents -> numpy grid through a3d_decode_host (see __call__)."""
+        _require_cuda()
+        z = np.ascontiguousarray(np.asarray(latents), dtype=np.float32).reshape(-1, self.input_dim)
+        n = z.shape[0]
+        code = OUT[out_dtype]
+        shape, dt = (((n, 64, 64, 64, 1), np.float32), ((n, 64, 64, 64, 1), np.float16), ((n, VOXELS // 8), np.uint8))[code]
+        if out is None:
+            out = np.empty(shape, dt)
+        elif out.dtype != dt or out.size != int(np.prod(shape)) or not out.flags['C_CONTIGUOUS']:
+            raise ValueError(f'out must be a C-contiguous {np.dtype(dt).name} array with {int(np.prod(shape))} elements')
+        torch = _torch()
+        with torch.cuda.device(self.device_index):
+            _capi.check(self._lib.a3d_decode_host(self._h, z.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p),
+                                                  code, float(threshold)), 'a3d_decode_host')
+        return out.reshape(shape)
 
     # ---- diagnostics
     def debug_layer(self, layer: int, n: int) -> np.ndarray:
@@ -278,59 +303,77 @@ def impute(decoder: Decoder3D, z, mask, category_vectors, K: int = 1, seed: int 
     return out, cstar
 
 
-_default_decoder_for_sampling: list = []
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory (for the ``out=`` / host-buffer calls: copies then run at the PCIe rate).
+    The memory is owned by a torch tensor kept alive by the array's base."""
+    torch = _require_cuda()
+    t = torch.empty(tuple(int(v) for v in np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
 
 
-def sampling(mu, logVar, seed: int | None = None, decoder: Decoder3D | None = None):
-    """function.py:35-38: mu + sqrt(exp(logVar)) * eps with eps ~ N(0,1) (Philox4x32-10 on the GPU).
-    The reference is unseeded; pass ``seed`` for reproducible draws."""
+def sampling(mu, logVar, seed: int | None = None, decoder: Decoder3D | None = None, obj_offset: int = 0):
+    """function.py:35-38: mu + sqrt(exp(logVar)) * eps with eps ~ N(0,1) (Philox4x32-10 + Box-Muller on the GPU,
+    a3d_sampling: one kernel, no handle).  The reference is unseeded; pass ``seed`` for reproducible draws (row b uses
+    the k = 0 stream of object ``obj_offset + b`` of the imputation sampler).  ``decoder`` only selects the device."""
     torch = _require_cuda()
     is_np = not isinstance(mu, torch.Tensor)
     dev = torch.device('cuda', torch.cuda.current_device()) if decoder is None else decoder.device
     mu_t = _as_dev_f32(mu, torch, dev)
     lv_t = _as_dev_f32(logVar, torch, dev)
-    shape = mu_t.shape
-    D = int(shape[-1])
-    if decoder is None or decoder.input_dim != D:
-        key = (D, dev.index)
-        hit = [d for k, d in _default_decoder_for_sampling if k == key]
-        if hit:
-            decoder = hit[0]
-        else:
-            from .presets import MODELNET_DECODER
-            decoder = Decoder3D(dict(MODELNET_DECODER, input_dim=D), max_chunk=32, device=dev.index)
-            _default_decoder_for_sampling.append((key, decoder))
+    if mu_t.shape != lv_t.shape:
+        raise ValueError('mu and logVar must have the same shape')
+    D = int(mu_t.shape[-1])
+    n = mu_t.numel() // max(D, 1)
     if seed is None:
         seed = int.from_bytes(os.urandom(8), 'little')
-    flat = mu_t.reshape(-1, D)
-    zeros = torch.zeros_like(flat)
-    eps, _ = impute(decoder, zeros, zeros, None, K=1, seed=seed, fill='normal')
-    out = mu_t + torch.sqrt(torch.exp(lv_t)) * eps.reshape(shape)
+    out = torch.empty_like(mu_t)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_sampling(mu_t.data_ptr(), lv_t.data_ptr(), n, D, seed, obj_offset, out.data_ptr(),
+                                             _stream_ptr(torch)), 'a3d_sampling')
     return out.cpu().numpy() if is_np else out
 
 
-def pack_targets(decoder: Decoder3D, targets):
+def nearest_prior(z, category_vectors, category_list=None, device=None):
+    """Nearest-prior classification of getEval (nolbo.py:1488-1494): argmin_c ||z_b - mu_c||^2 over all dims and, with
+    the one-hot ``category_list``, acc_cat = mean(argmin == argmax(category_list)).  Returns (idx int32 CUDA tensor [B],
+    acc float or None).  ``z`` may be [B, D] or [B, K, D] (the first of the K completed latents is classified)."""
+    torch = _require_cuda()
+    dev = z.device if isinstance(z, torch.Tensor) and z.is_cuda else (
+        torch.device('cuda', torch.cuda.current_device()) if device is None else device)
+    z_t = _as_dev_f32(z, torch, dev)
+    B, D = z_t.shape[0], z_t.shape[-1]
+    stride = z_t.numel() // max(B, 1)
+    mu = _as_dev_f32(category_vectors, torch, dev)
+    lab = None if category_list is None else _as_dev_f32(category_list, torch, dev)
+    idx = torch.empty((B,), dtype=torch.int32, device=dev)
+    hits = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_nearest_prior(z_t.data_ptr(), stride, mu.data_ptr(), mu.shape[0], D,
+                                                  0 if lab is None else lab.data_ptr(), B, idx.data_ptr(),
+                                                  0 if lab is None else hits.data_ptr(), _stream_ptr(torch)),
+                    'a3d_nearest_prior')
+    return idx, (None if lab is None else hits.item() / max(B, 1))
+
+
+def pack_targets(decoder: Decoder3D | None, targets):
     """fp32 {0,1} voxel targets [B,64,64,64,1] (loader layout) -> bit-packed [B, 32768] uint8 CUDA tensor."""
     torch = _require_cuda()
-    t = _as_dev_f32(targets, torch, decoder.device)
+    dev, hnd = _dev_and_handle(decoder, torch)
+    t = _as_dev_f32(targets, torch, dev)
     B = t.shape[0]
     V = t.numel() // B
-    bits = torch.empty((B, V // 8), dtype=torch.uint8, device=decoder.device)
-    with torch.cuda.device(decoder.device_index):
-        _capi.check(decoder._lib.a3d_pack_targets(decoder._h, t.data_ptr(), B, V, bits.data_ptr(), _stream_ptr(torch)),
+    bits = torch.empty((B, V // 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_pack_targets(hnd, t.data_ptr(), B, V, bits.data_ptr(), _stream_ptr(torch)),
                     'a3d_pack_targets')
     return bits
-
-
-_vpr_decoder: list = []
 
 
 def voxelPrecisionRecall(xTarget, xPred, prob: float = 0.5, decoder: Decoder3D | None = None):
     """function.py:100-115.  Returns (TP, FP, FN), each [B] float32 like the reference's float sums."""
     torch = _require_cuda()
     is_np = not isinstance(xPred, torch.Tensor)
-    decoder = decoder or _default_decoder()
-    dev = decoder.device
+    dev, hnd = _dev_and_handle(decoder, torch)
     t = _as_dev_f32(xTarget, torch, dev)
     p = _as_dev_f32(xPred, torch, dev)
     B = p.shape[0]
@@ -338,8 +381,8 @@ def voxelPrecisionRecall(xTarget, xPred, prob: float = 0.5, decoder: Decoder3D |
     if t.numel() != p.numel():
         raise ValueError('xTarget and xPred must have the same number of voxels')
     cnt = torch.empty((B, 3), dtype=torch.int64, device=dev)
-    with torch.cuda.device(decoder.device_index):
-        _capi.check(decoder._lib.a3d_counts(decoder._h, t.data_ptr(), p.data_ptr(), B, V, float(prob), cnt.data_ptr(),
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_counts(hnd, t.data_ptr(), p.data_ptr(), B, V, float(prob), cnt.data_ptr(),
                                             _stream_ptr(torch)), 'a3d_counts')
     f = cnt.to(torch.float32)
     tp, fp, fn = f[:, 0], f[:, 1], f[:, 2]
@@ -348,10 +391,11 @@ def voxelPrecisionRecall(xTarget, xPred, prob: float = 0.5, decoder: Decoder3D |
     return tp, fp, fn
 
 
-def _default_decoder():
-    if not _vpr_decoder:
-        _vpr_decoder.append(Decoder3D(presets.MODELNET_DECODER, max_chunk=32))
-    return _vpr_decoder[0]
+def _dev_and_handle(decoder, torch):
+    """The stand-alone scoring helpers need no decoder handle (the C entry points accept NULL)."""
+    if decoder is None:
+        return torch.device('cuda', torch.cuda.current_device()), None
+    return decoder.device, decoder._h
 
 
 def voxelPrecisionRecallSweep(xTarget, xPred, thresholds, strict: bool = True, decoder: Decoder3D | None = None):
@@ -359,16 +403,15 @@ def voxelPrecisionRecallSweep(xTarget, xPred, thresholds, strict: bool = True, d
     thresholds).  Returns int64 counts [B, T, 3] (TP, FP, FN) as a CUDA tensor (numpy if the inputs were numpy)."""
     torch = _require_cuda()
     is_np = not isinstance(xPred, torch.Tensor)
-    decoder = decoder or _default_decoder()
-    dev = decoder.device
+    dev, hnd = _dev_and_handle(decoder, torch)
     t = _as_dev_f32(xTarget, torch, dev)
     p = _as_dev_f32(xPred, torch, dev)
     B = p.shape[0]
     V = p.numel() // max(B, 1)
     thr = np.ascontiguousarray(thresholds, np.float32).reshape(-1)
     cnt = torch.empty((B, len(thr), 3), dtype=torch.int64, device=dev)
-    with torch.cuda.device(decoder.device_index):
-        _capi.check(decoder._lib.a3d_counts_sweep(decoder._h, t.data_ptr(), p.data_ptr(), B, V,
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_counts_sweep(hnd, t.data_ptr(), p.data_ptr(), B, V,
                                                   thr.ctypes.data_as(C.c_void_p), len(thr), int(strict), cnt.data_ptr(),
                                                   _stream_ptr(torch)), 'a3d_counts_sweep')
     return cnt.cpu().numpy() if is_np else cnt
@@ -382,15 +425,14 @@ def binary_loss(xPred, xTarget, epsilon: float = 1e-7, gamma: float = 0.5, b_ran
         raise NotImplementedError('binary_loss: only epsilon=1e-7, b_range=False (the reference call sites) are built')
     torch = _require_cuda()
     is_np = not isinstance(xPred, torch.Tensor)
-    decoder = decoder or _default_decoder()
-    dev = decoder.device
+    dev, hnd = _dev_and_handle(decoder, torch)
     p = _as_dev_f32(xPred, torch, dev)
     t = _as_dev_f32(xTarget, torch, dev)
     B = p.shape[0]
     V = p.numel() // max(B, 1)
     loss = torch.empty((B,), dtype=torch.float64, device=dev)
-    with torch.cuda.device(decoder.device_index):
-        _capi.check(decoder._lib.a3d_binary_loss(decoder._h, p.data_ptr(), t.data_ptr(), B, V, float(gamma),
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().a3d_binary_loss(hnd, p.data_ptr(), t.data_ptr(), B, V, float(gamma),
                                                  loss.data_ptr(), _stream_ptr(torch)), 'a3d_binary_loss')
     out = loss.to(torch.float32)
     return out.cpu().numpy() if is_np else out
@@ -494,8 +536,8 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
             mask = rng.choice(2, B * D, p=[missing_prob, 1. - missing_prob]).reshape(B, D).astype('float32')  # :1475
         fill0 = 'mean'
     else:
-        mask = np.ones((B, D), np.float32)   # :1485-1486
-        fill0 = 'mean'
+        mask = np.ones((B, D), np.float32)   # :1485-1486: no mask and no where(z == 0) fill on this branch
+        fill0 = 'none'
     bits = pack_targets(decoder, output_images)
     cat = None if category_list is None else _as_dev_f32(category_list, torch, decoder.device)
 
@@ -507,10 +549,8 @@ def getEval(decoder: Decoder3D, inputs, category_vectors, training: bool = False
         pr = (c[:, 0] / (c[:, 0] + c[:, 1] + 1e-10)).mean().item()   # :1499-1501
         rc = (c[:, 0] / (c[:, 0] + c[:, 2] + 1e-10)).mean().item()
         acc = None
-        if cat is not None:
-            zc = r['z_completed'][:, 0, :]
-            dist = ((zc[:, None, :] - mu[None]) ** 2).sum(-1)          # :1488-1494 (metric only; plumbing)
-            acc = (dist.argmin(-1) == cat.argmax(-1)).float().mean().item()
+        if cat is not None:                                             # :1488-1494 / :1511-1518
+            _, acc = nearest_prior(r['z_completed'], mu, cat)
         return r['mean_prob'], loss, pr, rc, acc
 
     pred, loss, pr, rc, acc = branch(fill0, 1)

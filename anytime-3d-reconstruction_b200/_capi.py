@@ -19,7 +19,8 @@ IO = {'fp16': 0, 'f16': 0, 'float16': 0, 'bf16': 1, 'bfloat16': 1, 'fp32': 2, 'f
 FINAL = {'None': 0, None: 0, 'linear': 0, 'sigmoid': 1}
 DTYPE = {'fp16': 0, 'f16': 0, 'float16': 0, 'bf16': 1, 'bfloat16': 1}
 IMPL = {'tcgen05': 0, 'simt': 1}
-FILL = {'prior_sample': 0, 'mean': 1, 'normal': 2}
+FILL = {'prior_sample': 0, 'mean': 1, 'normal': 2, 'none': 3}
+OUT = {'f32': 0, 'fp32': 0, 'float32': 0, 'f16': 1, 'fp16': 1, 'float16': 1, 'bits': 2}
 
 
 class Desc(C.Structure):
@@ -62,6 +63,10 @@ SIGNATURES = {
     'a3d_set_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     'a3d_get_weight': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     'a3d_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'a3d_decode_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float]),
+    'a3d_sampling': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    'a3d_nearest_prior': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'a3d_impute': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_uint64,
                              C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'a3d_anytime_eval': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float, C.c_void_p,

@@ -65,6 +65,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // and frees slot 3 first.  Equal consecutive phases are legal (the MMA warp just waits for the drains).
 __device__ __forceinline__ int start_phase(int d) { return (d & 2) ? 2 : 0; }
 
+// Output depth of item t for a class with depth parity pd.  pd = 1 classes run one plane behind (d = t - 1 mod 16):
+// class (pd, .) reads the input planes d + pd - 1 and d + pd, so with this shift ALL FOUR classes working on item t read
+// the same two planes (t - 1, t) at the same time (L2 reuse), and all four have their half-length item (one plane
+// outside the grid) at t = 0 mod 16, which keeps the clusters of an item in step.
+__device__ __forceinline__ int item_depth(int t, int pd) { return (t + (pd ? WIN - 1 : 0)) % WIN; }
+
 // ELU / ReLU / LeakyReLU / identity on a packed pair of fp32 values, then 16-bit pack.  ELU is branch- and
 // predicate-free: max(v, 2^min(v log2e, 0) - 1) equals v for v > 0 (the exponential term is 0) and exp(v) - 1 below
 // (exp(v) - 1 >= v everywhere); ex2.approx.ftz has 2^-22 relative error, i.e. <= 2.4e-7 absolute on exp(v) <= 1.
@@ -188,7 +194,7 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         ++w_loads;
         for (int k = 0; k < S.count; ++k) {
           const int t = S.first + k * S.stride;
-          const int d = t % WIN;
+          const int d = item_depth(t, pd);
           const int nb = 2 * (t / WIN) + (int)rank;
           for (int j = 0; j < WIN; ++j) {
             for (int sd = 0; sd < 2; ++sd) {
@@ -223,7 +229,7 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         ptx::tc_fence_after();
         for (int k = 0; k < S.count; ++k) {
           const int t = S.first + k * S.stride;
-          const int d = t % WIN;
+          const int d = item_depth(t, pd);
           int phi = start_phase(d);
           for (int j = 0; j < WIN; ++j, phi = (phi == 2) ? 0 : phi + 1) {
             const int s0 = phi, s1 = phi + 1;
@@ -373,7 +379,7 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       const int pd = S.q >> 1, ph = S.q & 1;
       for (int k = 0; k < S.count; ++k) {
         const int t = S.first + k * S.stride;
-        const int d = t % WIN;
+        const int d = item_depth(t, pd);
         const int nb = 2 * (t / WIN) + (int)rank;
         int phi = start_phase(d);
         for (int j = 0; j < WIN; ++j, phi = (phi == 2) ? 0 : phi + 1) {

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -110,6 +111,11 @@ struct a3d_handle {
   unsigned long long* st_counts = nullptr;
   int64_t st_B = 0, st_BK = 0, st_C = 0;
   bool st_has_mean = false;
+  // a3d_decode_host staging: latents, two fp32 grid buffers, two converted (fp16 / bit) buffers, copy stream, events
+  cudaStream_t copy_stream = nullptr;
+  float* dh_z = nullptr; int64_t dh_z_cap = 0;
+  float* dh_grid[2] = {nullptr, nullptr}; void* dh_out[2] = {nullptr, nullptr}; int64_t dh_sub_cap = 0;
+  cudaEvent_t dh_done[2] = {nullptr, nullptr}, dh_free[2] = {nullptr, nullptr};
   // bookkeeping
   int64_t launches = 0;
   bool profiling = false;
@@ -127,6 +133,13 @@ int check_handle(const a3d_handle* h) {
   if (!h) { set_error("null handle"); return A3D_ERR_INVALID; }
   if (h->sticky) { set_error("handle is in a sticky CUDA error state (%d)", h->sticky); return h->sticky; }
   return A3D_OK;
+}
+
+// the stand-alone scoring helpers accept a NULL handle (no sticky state, no launch counting)
+int check_opt(const a3d_handle* h) { return h ? check_handle(h) : A3D_OK; }
+int sticky_opt(a3d_handle* h, int rc) {
+  if (h && rc == A3D_ERR_CUDA) h->sticky = rc;
+  return rc;
 }
 
 // Keras variable table ------------------------------------------------------------------------------------------
@@ -287,6 +300,9 @@ int finalize_weights(a3d_handle* h) {
   const int fmt = h->desc.operand_dtype;
   int rc;
   std::vector<float> sc, sf;
+  // the uploads below overwrite live device buffers with synchronous copies: no earlier decode (on any caller stream) may
+  // still be reading them
+  if (h->d_wd) A3D_CUDA_OK(cudaDeviceSynchronize());
   // dense + BN0
   if ((rc = upload(h->w[0].data(), h->w[0].size() * 4, (void**)&h->d_wd))) return rc;
   if ((rc = upload(h->w[1].data(), h->w[1].size() * 4, (void**)&h->d_bd))) return rc;
@@ -514,8 +530,8 @@ int a3d_abi_version(void) { return A3D_ABI_VERSION; }
 
 uint32_t a3d_crc32c(const void* data, size_t n, uint32_t crc) {
   static uint32_t tbl[8][256];
-  static bool init = false;
-  if (!init) {
+  static std::once_flag once;     // loader workers may verify checkpoints concurrently
+  std::call_once(once, [] {
     for (uint32_t i = 0; i < 256; ++i) {
       uint32_t c = i;
       for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
@@ -523,8 +539,7 @@ uint32_t a3d_crc32c(const void* data, size_t n, uint32_t crc) {
     }
     for (uint32_t i = 0; i < 256; ++i)
       for (int t = 1; t < 8; ++t) tbl[t][i] = (tbl[t - 1][i] >> 8) ^ tbl[0][tbl[t - 1][i] & 0xFF];
-    init = true;
-  }
+  });
   const uint8_t* p = static_cast<const uint8_t*>(data);
   uint32_t c = crc ^ 0xFFFFFFFFu;
   while (n >= 8) {   // slice-by-8
@@ -615,6 +630,13 @@ void a3d_destroy(a3d_handle* h) {
   for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_sw); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
+  cudaFree(h->dh_z);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->dh_grid[i]); cudaFree(h->dh_out[i]);
+    if (h->dh_done[i]) cudaEventDestroy(h->dh_done[i]);
+    if (h->dh_free[i]) cudaEventDestroy(h->dh_free[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -686,8 +708,8 @@ int a3d_impute(a3d_handle* h, const float* z_dev, const float* mask_dev, const f
                void* stream) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if (B < 0 || K < 1 || fill_mode < 0 || fill_mode > 2 || (B > 0 && (!z_dev || !mask_dev || !z_out_dev)) ||
-      (fill_mode != A3D_FILL_NORMAL && (C < 1 || !mu_table_dev))) {
+  if (B < 0 || K < 1 || fill_mode < 0 || fill_mode > 3 || (B > 0 && (!z_dev || !mask_dev || !z_out_dev)) ||
+      (fill_mode != A3D_FILL_NORMAL && fill_mode != A3D_FILL_NONE && (C < 1 || !mu_table_dev))) {
     set_error("a3d_impute: bad arguments");
     return A3D_ERR_INVALID;
   }
@@ -741,7 +763,7 @@ int a3d_anytime_eval_loss(a3d_handle* h, const float* z_bkd_dev, int64_t B, int 
 
 int a3d_binary_loss(a3d_handle* h, const float* pred_dev, const float* target_dev, int64_t B, int64_t V, float gamma,
                     double* loss_dev, void* stream) {
-  int rc = check_handle(h);
+  int rc = check_opt(h);
   if (rc) return rc;
   if (B < 0 || V <= 0 || V % 4 != 0 || (B > 0 && (!pred_dev || !target_dev || !loss_dev))) {
     set_error("a3d_binary_loss: bad arguments (V must be a positive multiple of 4)");
@@ -749,12 +771,12 @@ int a3d_binary_loss(a3d_handle* h, const float* pred_dev, const float* target_de
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (B > 0) A3D_CUDA_OK(cudaMemsetAsync(loss_dev, 0, (size_t)B * sizeof(double), st));
-  return sticky(h, launch_binary_loss(pred_dev, target_dev, B, V, gamma, loss_dev, st, &h->launches));
+  return sticky_opt(h, launch_binary_loss(pred_dev, target_dev, B, V, gamma, loss_dev, st, h ? &h->launches : nullptr));
 }
 
 int a3d_counts_sweep(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V,
                      const float* thresholds, int T, int strict, int64_t* counts_dev, void* stream) {
-  int rc = check_handle(h);
+  int rc = check_opt(h);
   if (rc) return rc;
   if (B < 0 || V <= 0 || V % 4 != 0 || T < 1 || T > 32 || !thresholds ||
       (B > 0 && (!target_dev || !pred_dev || !counts_dev))) {
@@ -763,13 +785,13 @@ int a3d_counts_sweep(a3d_handle* h, const float* target_dev, const float* pred_d
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (B > 0) A3D_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)B * T * 3 * sizeof(int64_t), st));
-  return sticky(h, launch_counts_sweep(target_dev, pred_dev, B, V, thresholds, T, strict,
-                                       reinterpret_cast<unsigned long long*>(counts_dev), st, &h->launches));
+  return sticky_opt(h, launch_counts_sweep(target_dev, pred_dev, B, V, thresholds, T, strict,
+                                       reinterpret_cast<unsigned long long*>(counts_dev), st, h ? &h->launches : nullptr));
 }
 
 int a3d_counts(a3d_handle* h, const float* target_dev, const float* pred_dev, int64_t B, int64_t V, float thr,
                int64_t* counts_dev, void* stream) {
-  int rc = check_handle(h);
+  int rc = check_opt(h);
   if (rc) return rc;
   if (B < 0 || V <= 0 || V % 8 != 0 || (B > 0 && (!target_dev || !pred_dev || !counts_dev))) {
     set_error("a3d_counts: bad arguments (V must be a positive multiple of 8)");
@@ -777,18 +799,18 @@ int a3d_counts(a3d_handle* h, const float* target_dev, const float* pred_dev, in
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (B > 0) A3D_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)B * 3 * sizeof(int64_t), st));
-  return sticky(h, launch_counts(target_dev, pred_dev, B, V, thr, reinterpret_cast<unsigned long long*>(counts_dev), st,
-                                 &h->launches));
+  return sticky_opt(h, launch_counts(target_dev, pred_dev, B, V, thr, reinterpret_cast<unsigned long long*>(counts_dev), st,
+                                 h ? &h->launches : nullptr));
 }
 
 int a3d_pack_targets(a3d_handle* h, const float* target_dev, int64_t B, int64_t V, uint8_t* bits_dev, void* stream) {
-  int rc = check_handle(h);
+  int rc = check_opt(h);
   if (rc) return rc;
   if (B < 0 || V <= 0 || V % 8 != 0 || (B > 0 && (!target_dev || !bits_dev))) {
     set_error("a3d_pack_targets: bad arguments");
     return A3D_ERR_INVALID;
   }
-  return sticky(h, launch_pack(target_dev, B, V, bits_dev, (cudaStream_t)stream, &h->launches));
+  return sticky_opt(h, launch_pack(target_dev, B, V, bits_dev, (cudaStream_t)stream, h ? &h->launches : nullptr));
 }
 
 int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, const float* mu_table, int C, int64_t B,
@@ -806,17 +828,21 @@ int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, cons
     cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_bits);
     cudaFree(h->st_counts); cudaFree(h->st_mean);
     h->st_z = h->st_mask = h->st_mu = h->st_zout = h->st_mean = nullptr; h->st_bits = nullptr; h->st_counts = nullptr;
-    h->st_B = B > h->st_B ? B : h->st_B;
-    h->st_BK = B * K > h->st_BK ? B * K : h->st_BK;
-    h->st_C = C > h->st_C ? C : (h->st_C > 0 ? h->st_C : 1);
-    h->st_has_mean = h->st_has_mean || mean_prob_or_null != nullptr;
-    A3D_CUDA_OK(cudaMalloc(&h->st_z, (size_t)h->st_B * D * 4));
-    A3D_CUDA_OK(cudaMalloc(&h->st_mask, (size_t)h->st_B * D * 4));
-    A3D_CUDA_OK(cudaMalloc(&h->st_mu, (size_t)h->st_C * D * 4));
-    A3D_CUDA_OK(cudaMalloc(&h->st_zout, (size_t)h->st_BK * D * 4));
-    A3D_CUDA_OK(cudaMalloc(&h->st_bits, (size_t)h->st_B * (A3D_VOXELS / 8)));
-    A3D_CUDA_OK(cudaMalloc(&h->st_counts, (size_t)h->st_B * 3 * 8));
-    if (h->st_has_mean) A3D_CUDA_OK(cudaMalloc(&h->st_mean, (size_t)h->st_B * A3D_VOXELS * 4));
+    // the new capacities are committed only after every allocation succeeded: a failed cudaMalloc leaves the sizes at
+    // zero, so the next call allocates again instead of running on null staging pointers
+    const int64_t nB = B > h->st_B ? B : h->st_B, nBK = B * K > h->st_BK ? B * K : h->st_BK;
+    const int64_t nC = C > h->st_C ? C : (h->st_C > 0 ? h->st_C : 1);
+    const bool want_mean = h->st_has_mean || mean_prob_or_null != nullptr;
+    h->st_B = h->st_BK = h->st_C = 0;
+    h->st_has_mean = false;
+    A3D_CUDA_OK(cudaMalloc(&h->st_z, (size_t)nB * D * 4));
+    A3D_CUDA_OK(cudaMalloc(&h->st_mask, (size_t)nB * D * 4));
+    A3D_CUDA_OK(cudaMalloc(&h->st_mu, (size_t)nC * D * 4));
+    A3D_CUDA_OK(cudaMalloc(&h->st_zout, (size_t)nBK * D * 4));
+    A3D_CUDA_OK(cudaMalloc(&h->st_bits, (size_t)nB * (A3D_VOXELS / 8)));
+    A3D_CUDA_OK(cudaMalloc(&h->st_counts, (size_t)nB * 3 * 8));
+    if (want_mean) A3D_CUDA_OK(cudaMalloc(&h->st_mean, (size_t)nB * A3D_VOXELS * 4));
+    h->st_B = nB; h->st_BK = nBK; h->st_C = nC; h->st_has_mean = want_mean;
   }
   cudaStream_t st = h->own_stream;
   A3D_CUDA_OK(cudaMemcpyAsync(h->st_z, z, (size_t)B * D * 4, cudaMemcpyHostToDevice, st));
@@ -834,6 +860,100 @@ int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, cons
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("a3d_anytime_eval_host: %s", cudaGetErrorString(e));
+    h->sticky = A3D_ERR_CUDA;
+    return A3D_ERR_CUDA;
+  }
+  return A3D_OK;
+}
+
+int a3d_sampling(const float* mu_dev, const float* logvar_dev, int64_t n, int D, uint64_t seed, uint64_t obj_offset,
+                 float* z_dev, void* stream) {
+  if (n < 0 || D < 1 || (n > 0 && (!mu_dev || !logvar_dev || !z_dev))) { set_error("a3d_sampling: bad arguments"); return A3D_ERR_INVALID; }
+  return launch_sampling(mu_dev, logvar_dev, n, D, seed, obj_offset, z_dev, (cudaStream_t)stream, nullptr);
+}
+
+int a3d_nearest_prior(const float* z_dev, int64_t z_stride, const float* mu_table_dev, int C, int D,
+                      const float* labels_dev, int64_t B, int32_t* idx_out_dev, int32_t* hits_dev, void* stream) {
+  if (B < 0 || C < 1 || D < 1 || z_stride < D || (B > 0 && (!z_dev || !mu_table_dev)) || (hits_dev && !labels_dev)) {
+    set_error("a3d_nearest_prior: bad arguments");
+    return A3D_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hits_dev) A3D_CUDA_OK(cudaMemsetAsync(hits_dev, 0, sizeof(int32_t), st));
+  return launch_nearest_prior(z_dev, z_stride, mu_table_dev, C, D, labels_dev, B, idx_out_dev, hits_dev, st, nullptr);
+}
+
+int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_host, int out_dtype, float thr) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (n < 0 || out_dtype < A3D_OUT_F32 || out_dtype > A3D_OUT_BITS || (n > 0 && (!z_host || !out_host))) {
+    set_error("a3d_decode_host: bad arguments");
+    return A3D_ERR_INVALID;
+  }
+  if (n == 0) return A3D_OK;
+  if ((rc = sticky(h, finalize_weights(h)))) return rc;
+  const int D = h->desc.latent_dim;
+  // sub-chunk: small enough that the first (un-overlapped) decode is short against the copies, large enough to keep the
+  // decoder kernels efficient; a sub-chunk's D2H copy (1 MiB per fp32 grid) takes ~3x its decode time
+  int64_t sub = n <= 512 ? 16 : (n <= 2048 ? 64 : 256);
+  if (sub > h->max_chunk) sub = h->max_chunk;
+  if (!h->copy_stream) {
+    A3D_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      A3D_CUDA_OK(cudaEventCreateWithFlags(&h->dh_done[i], cudaEventDisableTiming));
+      A3D_CUDA_OK(cudaEventCreateWithFlags(&h->dh_free[i], cudaEventDisableTiming));
+    }
+  }
+  if (n > h->dh_z_cap) {
+    cudaFree(h->dh_z); h->dh_z = nullptr; h->dh_z_cap = 0;
+    A3D_CUDA_OK(cudaMalloc(&h->dh_z, (size_t)n * D * 4));
+    h->dh_z_cap = n;
+  }
+  if (sub > h->dh_sub_cap) {
+    for (int i = 0; i < 2; ++i) { cudaFree(h->dh_grid[i]); cudaFree(h->dh_out[i]); h->dh_grid[i] = nullptr; h->dh_out[i] = nullptr; }
+    h->dh_sub_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+      A3D_CUDA_OK(cudaMalloc(&h->dh_grid[i], (size_t)sub * A3D_VOXELS * 4));
+      A3D_CUDA_OK(cudaMalloc(&h->dh_out[i], (size_t)sub * A3D_VOXELS * 2));
+    }
+    h->dh_sub_cap = sub;
+  }
+  cudaStream_t cs = h->own_stream, ps = h->copy_stream;
+  const size_t per = out_dtype == A3D_OUT_F32 ? (size_t)A3D_VOXELS * 4 : out_dtype == A3D_OUT_F16 ? (size_t)A3D_VOXELS * 2
+                                                                                               : (size_t)A3D_VOXELS / 8;
+  A3D_CUDA_OK(cudaMemcpyAsync(h->dh_z, z_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, cs));
+  const int64_t nsub = (n + sub - 1) / sub;
+  auto compute = [&](int64_t i) -> int {
+    const int b = (int)(i & 1);
+    const int64_t off = i * sub, nc = (n - off < sub) ? n - off : sub;
+    if (i >= 2) A3D_CUDA_OK(cudaStreamWaitEvent(cs, h->dh_free[b], 0));
+    int r = sticky(h, run_hidden(h, h->dh_z + off * D, nc, cs));
+    if (r) return r;
+    if ((r = sticky(h, run_tail(h, nc, 1, nullptr, thr, nullptr, h->dh_grid[b], 0.f, nullptr, cs)))) return r;
+    if (out_dtype != A3D_OUT_F32 &&
+        (r = sticky(h, launch_grid_convert(h->dh_grid[b], nc * (int64_t)A3D_VOXELS, out_dtype, thr, h->dh_out[b], cs,
+                                           &h->launches))))
+      return r;
+    A3D_CUDA_OK(cudaEventRecord(h->dh_done[b], cs));
+    return A3D_OK;
+  };
+  if ((rc = compute(0))) return rc;
+  for (int64_t i = 0; i < nsub; ++i) {
+    // queue the next decode BEFORE this sub-chunk's copy: with a pageable out_host the copy blocks the host, and the
+    // GPU should be busy meanwhile
+    if (i + 1 < nsub && (rc = compute(i + 1))) return rc;
+    const int b = (int)(i & 1);
+    const int64_t off = i * sub, nc = (n - off < sub) ? n - off : sub;
+    A3D_CUDA_OK(cudaStreamWaitEvent(ps, h->dh_done[b], 0));
+    const void* src = out_dtype == A3D_OUT_F32 ? (const void*)h->dh_grid[b] : (const void*)h->dh_out[b];
+    A3D_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + (size_t)off * per, src, (size_t)nc * per,
+                                cudaMemcpyDeviceToHost, ps));
+    A3D_CUDA_OK(cudaEventRecord(h->dh_free[b], ps));
+  }
+  cudaError_t e = cudaStreamSynchronize(ps);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+  if (e != cudaSuccess) {
+    set_error("a3d_decode_host: %s", cudaGetErrorString(e));
     h->sticky = A3D_ERR_CUDA;
     return A3D_ERR_CUDA;
   }

@@ -88,6 +88,12 @@ int launch_counts_sweep(const float* target, const float* pred, int64_t B, int64
                         unsigned long long* counts, cudaStream_t st, int64_t* launches);
 int launch_impute(const float* z, const float* mask, const float* mu, int C, int64_t B, int K, int D, uint64_t seed,
                   uint64_t obj_offset, int fill, float* z_out, int32_t* cstar, cudaStream_t st, int64_t* launches);
+int launch_sampling(const float* mu, const float* logvar, int64_t n, int D, uint64_t seed, uint64_t obj_offset, float* z,
+                    cudaStream_t st, int64_t* launches);
+int launch_nearest_prior(const float* z, int64_t z_stride, const float* mu, int C, int D, const float* labels, int64_t B,
+                         int32_t* idx, int32_t* hits, cudaStream_t st, int64_t* launches);
+int launch_grid_convert(const float* in, int64_t voxels, int out_dtype, float thr, void* out, cudaStream_t st,
+                        int64_t* launches);
 int launch_counts(const float* target, const float* pred, int64_t B, int64_t V, float thr,
                   unsigned long long* counts, cudaStream_t st, int64_t* launches);
 int launch_pack(const float* target, int64_t B, int64_t V, uint8_t* bits, cudaStream_t st, int64_t* launches);

@@ -40,7 +40,9 @@ enum { A3D_ACT_NONE = 0, A3D_ACT_ELU = 1, A3D_ACT_RELU = 2, A3D_ACT_LRELU = 3 /*
 enum { A3D_FINAL_NONE = 0, A3D_FINAL_SIGMOID = 1 };
 enum { A3D_DTYPE_F16 = 0, A3D_DTYPE_BF16 = 1 };          /* operand type of the tensor-core layers */
 enum { A3D_IMPL_TCGEN05 = 0, A3D_IMPL_SIMT = 1 };        /* SIMT = CUDA-core kernels, bring-up/diagnostic only */
-enum { A3D_FILL_PRIOR_SAMPLE = 0, A3D_FILL_MEAN = 1, A3D_FILL_NORMAL = 2 };
+enum { A3D_FILL_PRIOR_SAMPLE = 0, A3D_FILL_MEAN = 1, A3D_FILL_NORMAL = 2,
+       A3D_FILL_NONE = 3 /* z * mask only: getEval's missing_prob == 0 branch, nolbo.py:1485-1486 */ };
+enum { A3D_OUT_F32 = 0, A3D_OUT_F16 = 1, A3D_OUT_BITS = 2 };   /* grid formats of a3d_decode_host */
 
 /* Mirrors the `structure` dict consumed by decoder3D(structure), src/net_core/autoencoder3D.py:104-112. */
 typedef struct {
@@ -79,6 +81,28 @@ int a3d_get_weight(const a3d_handle* h, int index, float* host, size_t nbytes);
  * z_dev: [n, latent_dim] fp32 on the device; prob_dev: [n, 64,64,64,1] fp32 (NDHWC, like the Keras output). */
 int a3d_decode(a3d_handle* h, const float* z_dev, int64_t n, float* prob_dev, void* stream);
 
+/* decoder(z, training=False) as the reference's scripts use it: numpy latents in, the full occupancy grid back on the
+ * host (src/module/nolbo.py:1496 -> test_modelnet_VAE_dr.py:128-130 pulls the [72,64,64,64,1] prediction every iteration).
+ * z_host: [n, latent_dim] fp32; out_host: [n, 262144] of out_dtype -- A3D_OUT_F32 (the Keras output), A3D_OUT_F16
+ * (same values rounded to fp16, half the PCIe bytes) or A3D_OUT_BITS ([n, 32768] bytes, bit = p >= thr, packed like
+ * the targets).  The call is processed in sub-chunks on internal streams: the device->host copy of sub-chunk i runs
+ * while sub-chunk i+1 decodes (double-buffered staging), so with a PINNED out_host the call runs at the PCIe rate;
+ * pageable buffers work too (the copies then serialise in the driver).  Synchronous. */
+int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_host, int out_dtype, float thr);
+
+/* sampling(mu, logVar)                      src/module/function.py:35-38: z = mu + sqrt(exp(logVar)) * eps with
+ * eps ~ N(0,1) from Philox4x32-10 + Box-Muller, counter (dim/4, 0, obj_offset + row), key = seed (the k = 0 stream of
+ * a3d_impute).  mu_dev, logvar_dev, z_dev: [n, D] fp32 on the current device.  No handle needed. */
+int a3d_sampling(const float* mu_dev, const float* logvar_dev, int64_t n, int D, uint64_t seed, uint64_t obj_offset,
+                 float* z_dev, void* stream);
+
+/* Nearest-prior classification of getEval   src/module/nolbo.py:1488-1494,1511-1518: idx[b] = argmin_c ||z_b - mu_c||^2
+ * over ALL dims (tf.argmin: first minimum); with labels_dev ([B, C] one-hot category_list) *hits_dev receives the number
+ * of b with idx[b] == argmax_c labels[b, c], i.e. acc_cat * B (overwritten).  z rows are z_stride floats apart (pass
+ * K * D to classify the first of K completed latents per object).  idx_out_dev / labels_dev / hits_dev may be NULL. */
+int a3d_nearest_prior(const float* z_dev, int64_t z_stride, const float* mu_table_dev, int C, int D,
+                      const float* labels_dev, int64_t B, int32_t* idx_out_dev, int32_t* hits_dev, void* stream);
+
 /* sampling() + mask / fill logic           src/module/function.py:35-38; src/module/nolbo.py:1472-1486 (mean fill),
  * :1505-1510 (nearest-prior sample fill), :431-439 (N(0,1) fill).  K Philox4x32-10 normal draws per object are
  * scattered into the missing dims.  z, mask: [B, D]; mu_table: [C, D] (category_vectors); z_out: [B, K, D];
@@ -101,7 +125,10 @@ int a3d_anytime_eval_loss(a3d_handle* h, const float* z_bkd_dev, int64_t B, int 
                           float thr, float gamma, int64_t* counts_dev, double* loss_dev, float* mean_prob_dev,
                           void* stream);
 
-/* binary_loss(xPred, xTarget, epsilon = 1e-7, gamma)   src/module/function.py:73-82 (b_range = False), stand-alone form on
+/* The four stand-alone scoring helpers below need no decoder: `h` may be NULL (the current CUDA device is used and
+ * there is no launch counting / sticky state).
+ *
+ * binary_loss(xPred, xTarget, epsilon = 1e-7, gamma)   src/module/function.py:73-82 (b_range = False), stand-alone form on
  * fp32 grids [B, V]; loss_dev [B] double. */
 int a3d_binary_loss(a3d_handle* h, const float* pred_dev, const float* target_dev, int64_t B, int64_t V, float gamma,
                     double* loss_dev, void* stream);

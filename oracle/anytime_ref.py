@@ -103,6 +103,7 @@ def impute(z: np.ndarray, mask: np.ndarray, mu_table: np.ndarray, K: int, seed: 
     prior_sample  nolbo.py:1505-1510: on top of the mean fill, c* = argmin_c sum_d mask*(z-mu_c)^2 and the
                   missing dims (mask == 0) get N(mu_c*, 1) draws.
     normal        nolbo.py:431-439:   where(z*mask == 0) <- N(0, 1).
+    none          nolbo.py:1485-1486: the missing_prob == 0 branch: mask of ones, no fill at all (z * mask).
     """
     z = np.asarray(z, np.float32)
     mask = np.asarray(mask, np.float32)
@@ -111,6 +112,9 @@ def impute(z: np.ndarray, mask: np.ndarray, mu_table: np.ndarray, K: int, seed: 
     zm = z * mask
     out = np.empty((B, K, D), np.float32)
     cstar = np.full((B,), -1, np.int32)
+    if fill == 'none':
+        out[:] = zm[:, None, :]
+        return out, cstar
     if fill == 'normal':
         eps = philox_normals(seed, obj, K, D).astype(np.float32)
         out[:] = np.where(zm[:, None, :] == 0, eps, zm[:, None, :])
@@ -128,6 +132,15 @@ def impute(z: np.ndarray, mask: np.ndarray, mu_table: np.ndarray, K: int, seed: 
     prior = (mu[cstar][:, None, :].astype(np.float64) + eps).astype(np.float32)   # sampling(mu_c*, logVar=0)
     out[:] = np.where(mask[:, None, :] == 0, prior, zf[:, None, :])
     return out, cstar
+
+
+def nearest_prior(z: np.ndarray, mu_table: np.ndarray, category_list: np.ndarray | None = None):
+    """nolbo.py:1488-1494: argmin_c sum_d (z - mu_c)^2 over all dims; acc_cat = mean(argmin == argmax(category_list))."""
+    z = np.asarray(z, np.float64)
+    mu = np.asarray(mu_table, np.float64)
+    idx = ((z[:, None, :] - mu[None]) ** 2).sum(-1).argmin(-1).astype(np.int32)
+    acc = None if category_list is None else float((idx == np.asarray(category_list).argmax(-1)).mean())
+    return idx, acc
 
 
 def make_targets(rng: np.random.Generator, B: int, G: int = 64) -> np.ndarray:
