@@ -46,7 +46,7 @@ constexpr int TMEM_COLS = NSLOT * SLOT_COLS;    // 512
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int NUM_BARS = 2 * A_STAGES + 2 * NSLOT + 1;
-constexpr int SMEM_BYTES = 1024 + W_BYTES + A_STAGES * A_BYTES + OUT_STAGE_BYTES + NUM_BARS * 8 + 16 + 2 * COUT * 4;
+constexpr int SMEM_BYTES = 1024 + W_BYTES + A_STAGES * A_BYTES + OUT_STAGE_BYTES + NUM_BARS * 8 + 16 + 2 * COUT * 4 + 16;
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   const uint32_t z = 0;
@@ -60,10 +60,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // Phase (0 = A, 2 = C) in which the sweep of an item starts.  A function of the item's depth only, so that the split of
 // an output's accumulation into two partial sums (slot 3 + slot 0, fp32) depends on WHERE the output voxel is and
 // never on its decode's position in the batch: a latent decodes to bit-identical values in any batch / shard.
-// Regular clusters step d by 2 from item to item (18 clusters per class on 148 SMs), so consecutive items alternate
-// A, C: an item that ends in phase C leaves slots 0,1 free for a start in A, and one that ends in A has drained slot 2
-// and frees slot 3 first.  Equal consecutive phases are legal (the MMA warp just waits for the drains).
-__device__ __forceinline__ int start_phase(int d) { return (d & 2) ? 2 : 0; }
+// Regular clusters step d by 3 from item to item (round k -> k + 1 advances the item by per + 1 = 19 on 148 SMs), the
+// helper clusters by 1, so consecutive items alternate A, C: an item that ends in phase C leaves slots 0,1 free for a
+// start in A, and one that ends in A has drained slot 2 and frees slot 3 first.  Equal consecutive phases are legal (the
+// MMA warp just waits for the drains).
+__device__ __forceinline__ int start_phase(int d) { return (d & 1) ? 2 : 0; }
 
 // Output depth of item t for a class with depth parity pd.  pd = 1 classes run one plane behind (d = t - 1 mod 16):
 // class (pd, .) reads the input planes d + pd - 1 and d + pd, so with this shift ALL FOUR classes working on item t read
@@ -95,28 +96,49 @@ __device__ __forceinline__ uint32_t act_pack2(uint64_t y) {
   return pack2<FMT>(a, b);
 }
 
-// Work list of a cluster: up to two segments (parity class, first item, item stride, item count).  The regular clusters
-// own one class for the whole launch; the clusters left over after dividing the grid by four help two classes each.
-struct Seg { int q, first, stride, count; };
+constexpr int kPaceStride = 64;    // ints between two clusters' counters: one 256-byte L2 line pair (own slice) per counter
+constexpr long long kPaceTimeout = 300000;   // clocks (~0.2 ms) a producer waits for its peers before it goes on alone for a while
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Work list of a cluster: up to two segments.  The regular clusters own one parity class for the whole launch and walk
+// the items [0, limit) of that class in rounds of `per` items; the clusters left over after dividing the grid by four
+// help two classes each with the contiguous tail [first, first + count).
+//   Regular cluster cj takes item k * per + (cj + k) % per in round k: neighbouring clusters always work on neighbouring
+// items (they share an activation plane through L2), and the rotation by k walks every cluster through all 16 depths --
+// with the plain stride-`per` walk (per = 18) the half-length border items (one input plane outside the grid) all went to
+// the even-numbered clusters, which then idled 6 % of the launch.
+struct Seg { int q, first, count, per, cj, limit; };   // per > 0: regular (rounds); per == 0: contiguous tail
 struct Sched { Seg s[2]; };
+
+__device__ __forceinline__ int seg_item(const Seg& S, int k) {
+  if (S.per == 0) return S.first + k;
+  const int t = k * S.per + (S.cj + k) % S.per;
+  return t < S.limit ? t : -1;             // only the last round can be incomplete
+}
 
 __device__ __forceinline__ Sched make_sched(int cluster_id, int n_clusters, int n_items) {
   Sched sc;
   const int per = n_clusters >> 2;          // regular clusters per class (the launcher passes 4k or 4k + 2 clusters)
   const int reg = per << 2;
-  sc.s[1] = Seg{0, 0, 1, 0};
+  sc.s[1] = Seg{0, 0, 0, 0, 0, 0};
   // With two helper clusters, each helper finishes two classes: the regular clusters of a class walk items [0, n_reg),
   // the helper the tail [n_reg, n_items); n_reg / per = 2 (n_items - n_reg) balances both kinds of cluster.
   int n_reg = n_items;
   if (n_clusters > reg) n_reg = (int)(((long long)n_items * 2 * per + 2 * per) / (2 * per + 1));
   if (n_reg > n_items) n_reg = n_items;
   if (cluster_id < reg) {
-    const int first = cluster_id >> 2;
-    sc.s[0] = Seg{cluster_id & 3, first, per, n_reg > first ? (n_reg - first + per - 1) / per : 0};
+    sc.s[0] = Seg{cluster_id & 3, 0, (n_reg + per - 1) / per, per, cluster_id >> 2, n_reg};
   } else {
     const int e = cluster_id - reg;         // 0 or 1
-    sc.s[0] = Seg{2 * e, n_reg, 1, n_items - n_reg};
-    sc.s[1] = Seg{2 * e + 1, n_reg, 1, n_items - n_reg};
+    sc.s[0] = Seg{2 * e, n_reg, n_items - n_reg, 0, 0, n_items};
+    sc.s[1] = Seg{2 * e + 1, n_reg, n_items - n_reg, 0, 0, n_items};
   }
   return sc;
 }
@@ -125,7 +147,7 @@ template <int FMT, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_wgt,
                    uint16_t* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int n_blocks, int n_alloc) {
+                   int n_blocks, int n_alloc, int* __restrict__ progress, int pace_delta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
@@ -140,6 +162,8 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);   // 17 barriers + 8 bytes: 16-byte aligned for the float4 reads
   float* s_shift = s_scale + COUT;
+  volatile int* pace_allowed = reinterpret_cast<volatile int*>(s_shift + COUT);   // last step the producer may issue
+  volatile int* pace_done = pace_allowed + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,9 +172,14 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   const int n_items = ((n_blocks + 1) >> 1) * WIN;    // (decode-block pair, d)
   const Sched sched = make_sched(cluster_id, gridDim.x >> 1, n_items);
 
+  // pacing (see the producer): leader CTAs of the regular clusters only
+  const int n_reg_per = (int)(gridDim.x >> 3);
+  const bool pace_on = progress != nullptr && rank == 0 && cluster_id < 4 * n_reg_per && n_reg_per > 1;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_act);
     ptx::prefetch_tmap(&tmap_wgt);
+    *pace_allowed = (pace_delta & 256) ? -1 : (pace_delta & 255);   // staggered followers wait for the first poll
+    *pace_done = 0;
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < A_STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
@@ -176,6 +205,16 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t a_it = 0, w_loads = 0;
+      // Soft pacing of the regular clusters (L2 reuse): an activation plane is read by the four class clusters of an item
+      // and by the four of the next item (the clusters with the neighbouring index cj), 8 TMA loads of the same bytes.
+      // They only hit L2 if they happen within its retention time (~20 us at this kernel's 3 TB/s of fills), and nothing
+      // keeps 72 free-running clusters that close for 12 ms.  So the leader producer publishes the number of sweep steps
+      // it has issued, the otherwise idle warp 3 polls the counters of the class mates and of one cluster of each
+      // neighbouring group and keeps `pace_allowed` = slowest peer + pace_delta in shared memory, and the producer does
+      // not issue step s before pace_allowed >= s.  The slowest cluster never waits (no deadlock among resident CTAs); a
+      // wait longer than kPaceTimeout clocks (a peer that has not started yet, CTAs not co-resident) suspends pacing for 64 steps.
+      bool pace = pace_on && !(pace_delta & 512);   // bit 9 (diagnostic): publish and poll, never wait
+      int pace_step = 0, pace_resume = 0;
       for (int sg = 0; sg < 2; ++sg) {
         const Seg S = sched.s[sg];
         if (S.count == 0) continue;
@@ -193,10 +232,16 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           ptx::tma_load_2d_2sm(smem_w + j * 32768, &tmap_wgt, w_full, 0, wrow0 + j * 256);
         ++w_loads;
         for (int k = 0; k < S.count; ++k) {
-          const int t = S.first + k * S.stride;
+          const int t = seg_item(S, k);
+          if (t < 0) continue;
           const int d = item_depth(t, pd);
           const int nb = 2 * (t / WIN) + (int)rank;
-          for (int j = 0; j < WIN; ++j) {
+          for (int j = 0; j < WIN; ++j, ++pace_step) {
+            if (pace && pace_step >= pace_resume && *pace_allowed < pace_step) {
+              const long long t0 = clock64();
+              while (*pace_allowed < pace_step)
+                if (clock64() - t0 > kPaceTimeout) { pace_resume = pace_step + 64; break; }   // peer not running: retry later
+            }
             for (int sd = 0; sd < 2; ++sd) {
               const int id = d + sd - 1 + pd;
               if (id < 0 || id >= WIN) continue;
@@ -208,8 +253,14 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                 ptx::tma_load_5d_2sm(smem_a + as * A_BYTES, &tmap_act, &a_full[as], c * 64, nb * NT, -1, j, id);
               }
             }
+            if (pace_on) st_relaxed_gpu(progress + cluster_id * kPaceStride, pace_step + 1);
           }
         }
+      }
+      // done: nobody may wait for this cluster any more, and its poller can stop
+      if (pace_on) {
+        st_relaxed_gpu(progress + cluster_id * kPaceStride, 0x7fffffff);
+        *pace_done = 1;
       }
     }
   } else if (warp == 1) {
@@ -228,7 +279,8 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         ++w_loads;
         ptx::tc_fence_after();
         for (int k = 0; k < S.count; ++k) {
-          const int t = S.first + k * S.stride;
+          const int t = seg_item(S, k);
+          if (t < 0) continue;
           const int d = item_depth(t, pd);
           int phi = start_phase(d);
           for (int j = 0; j < WIN; ++j, phi = (phi == 2) ? 0 : phi + 1) {
@@ -269,6 +321,31 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             __syncwarp();
           }
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================== pacing poller (see the producer)
+    if (pace_on) {
+      const int my_q = cluster_id & 3, my_cj = cluster_id >> 2;
+      const int delta = pace_delta & 255;
+      const bool stagger = (pace_delta & 256) != 0;
+      int peer = -1, peer_lag = 0;
+      if (lane < 3) { const int q = (my_q + 1 + lane) & 3; peer = my_cj * 4 + q; peer_lag = (my_cj & 1) + (q != 0); }
+      else if (lane == 3) { const int c = (my_cj + n_reg_per - 1) % n_reg_per; peer = c * 4 + my_q; peer_lag = (c & 1) + (my_q != 0); }
+      else if (lane == 4) { const int c = (my_cj + 1) % n_reg_per; peer = c * 4 + my_q; peer_lag = (c & 1) + (my_q != 0); }
+      const int my_lag = (my_cj & 1) + (my_q != 0);
+      // a peer that leads this cluster in the staggered order must be a full step ahead (its loads have landed in L2);
+      // every other peer bounds how far this cluster may run ahead
+      const int slack = (stagger && peer_lag < my_lag) ? -2 : delta;
+      while (*pace_done == 0) {
+        int v = 0x7fffffff;
+        if (peer >= 0) {
+          const int p = ld_relaxed_gpu(progress + peer * kPaceStride);
+          v = p > 0x3fffffff ? 0x7fffffff : p + slack;
+        }
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (lane == 0) *pace_allowed = v;
+        __nanosleep(1000);   // ~1 M polls/s per counter line: an L2 slice must not become a hot spot
       }
     }
   } else if (warp >= 4) {
@@ -378,7 +455,8 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       if (S.count == 0) continue;
       const int pd = S.q >> 1, ph = S.q & 1;
       for (int k = 0; k < S.count; ++k) {
-        const int t = S.first + k * S.stride;
+        const int t = seg_item(S, k);
+        if (t < 0) continue;
         const int d = item_depth(t, pd);
         const int nb = 2 * (t / WIN) + (int)rank;
         int phi = start_phase(d);
@@ -407,11 +485,13 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 
 }  // namespace
 
+constexpr int kProgressInts = 128 * kPaceStride;
+size_t convt_l4_sw_progress_bytes() { return kProgressInts * sizeof(int); }
 size_t convt_l4_sw_weight_rows() { return (size_t)4 * 2 * (W_BYTES / 128); }
 
 int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
-                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
-                       cudaStream_t st, int64_t* launches) {
+                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, int* progress,
+                       int pace_delta, cudaStream_t st, int64_t* launches) {
   const int n_blocks = (int)((n + NT - 1) / NT);
   const int n_items = ((n_blocks + 1) / 2) * WIN;
   // 4k clusters (k per output-parity class) or 4k + 2: the two left-over clusters help two classes each
@@ -419,10 +499,14 @@ int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt,
   if ((n_clusters & 3) != 2 || n_items < 64) n_clusters &= ~3;
   if (n_clusters > 4 * n_items) n_clusters = 4 * n_items;
   if (n_clusters < 4) n_clusters = 4;
+  // pacing needs every cluster resident at once (true for a grid of <= num_sms CTAs on an otherwise idle GPU) and only
+  // pays when the launch is long enough for the clusters to drift apart
+  if (n_items < 8 * (n_clusters / 4) || 2 * n_clusters > num_sms || (pace_delta & 255) <= 0) progress = nullptr;
+  if (progress) A3D_CUDA_OK(cudaMemsetAsync(progress, 0, kProgressInts * sizeof(int), st));
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<2 * n_clusters, kThreads, SMEM_BYTES, st>>>(tmap_act, tmap_wgt, reinterpret_cast<uint16_t*>(out), scale,
-                                                       shift, n_blocks, (int)n_alloc);
+                                                       shift, n_blocks, (int)n_alloc, progress, pace_delta);
     A3D_CUDA_OK(cudaGetLastError());
     return A3D_OK;
   };

@@ -122,6 +122,9 @@ struct a3d_handle {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[5] = {0, 0, 0, 0, 0};
   int sticky = 0;
+  int* d_progress = nullptr; // pacing counters of the w-sweep kernel (one int per cluster)
+  int l4_pace = 8;           // sweep steps a cluster may run ahead of its peers (soft pacing, convt_l4_sw.cu);
+                             // A3D_L4_PACE=<n> overrides, 0 switches pacing off
   int l4_impl = 0;           // 128->64 layer: 0 = w-sweep 2-CTA kernel (convt_l4_sw.cu, default); A3D_L4_IMPL=ws: the
                              // round-1 h-sweep kernel (convt_l4_ws.cu); A3D_L4_IMPL=generic: the 1-CTA kernel of the other
                              // stride-2 layers (cross-checks; all three are parity-identical up to summation order)
@@ -130,13 +133,22 @@ struct a3d_handle {
 namespace {
 
 int check_handle(const a3d_handle* h) {
+  // The launch wrappers test cudaGetLastError() after every kernel launch.  That slot is process-wide and other runtime
+  // users (torch; the driver's staging path of a pageable cudaMemcpyAsync) can leave a benign, non-sticky error in it:
+  // drop it here so that it is not mistaken for a failure of the first launch of this call.  Sticky errors (an illegal
+  // access, a trap) come back on every later call anyway.
+  cudaGetLastError();
   if (!h) { set_error("null handle"); return A3D_ERR_INVALID; }
   if (h->sticky) { set_error("handle is in a sticky CUDA error state (%d)", h->sticky); return h->sticky; }
   return A3D_OK;
 }
 
 // the stand-alone scoring helpers accept a NULL handle (no sticky state, no launch counting)
-int check_opt(const a3d_handle* h) { return h ? check_handle(h) : A3D_OK; }
+int check_opt(const a3d_handle* h) {
+  if (h) return check_handle(h);
+  cudaGetLastError();
+  return A3D_OK;
+}
 int sticky_opt(a3d_handle* h, int rc) {
   if (h && rc == A3D_ERR_CUDA) h->sticky = rc;
   return rc;
@@ -480,7 +492,7 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
       rc = launch_convt_s2_simt(h->conv[li], h->act[li + 1], h->act[li + 2], n, fmt, act, st, &h->launches);
     else if (li == 2 && h->l4_impl == 0)
       rc = launch_convt_l4_sw(h->conv[li].tmap_act_sw, h->conv[li].tmap_wgt_sw, h->act[li + 2], h->conv[li].scale,
-                              h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
+                              h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, h->d_progress, h->l4_pace, st, &h->launches);
     else if (li == 2 && h->l4_impl == 1)
       rc = launch_convt_l4_ws(h->conv[li].tmap_act, h->conv[li].tmap_wgt_ws, h->act[li + 2], h->conv[li].scale,
                               h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
@@ -599,6 +611,12 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
   { const char* e = getenv("A3D_L4_IMPL"); h->l4_impl = !e ? 0 : std::string(e) == "generic" ? 2 : std::string(e) == "ws" ? 1 : 0; }
+  { const char* e = getenv("A3D_L4_PACE"); if (e) h->l4_pace = atoi(e); }
+  if (cudaMalloc(&h->d_progress, convt_l4_sw_progress_bytes()) != cudaSuccess) {
+    set_error("allocation of the pacing counters failed");
+    a3d_destroy(h);
+    return A3D_ERR_CUDA;
+  }
   { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; h->tail_pair = e && std::string(e) == "pair"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
@@ -630,6 +648,7 @@ void a3d_destroy(a3d_handle* h) {
   for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_sw); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
+  cudaFree(h->d_progress);
   cudaFree(h->dh_z);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->dh_grid[i]); cudaFree(h->dh_out[i]);
@@ -869,6 +888,7 @@ int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, cons
 int a3d_sampling(const float* mu_dev, const float* logvar_dev, int64_t n, int D, uint64_t seed, uint64_t obj_offset,
                  float* z_dev, void* stream) {
   if (n < 0 || D < 1 || (n > 0 && (!mu_dev || !logvar_dev || !z_dev))) { set_error("a3d_sampling: bad arguments"); return A3D_ERR_INVALID; }
+  cudaGetLastError();
   return launch_sampling(mu_dev, logvar_dev, n, D, seed, obj_offset, z_dev, (cudaStream_t)stream, nullptr);
 }
 
@@ -879,6 +899,7 @@ int a3d_nearest_prior(const float* z_dev, int64_t z_stride, const float* mu_tabl
     return A3D_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  cudaGetLastError();
   if (hits_dev) A3D_CUDA_OK(cudaMemsetAsync(hits_dev, 0, sizeof(int32_t), st));
   return launch_nearest_prior(z_dev, z_stride, mu_table_dev, C, D, labels_dev, B, idx_out_dev, hits_dev, st, nullptr);
 }
@@ -905,7 +926,8 @@ int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_hos
     }
   }
   if (n > h->dh_z_cap) {
-    cudaFree(h->dh_z); h->dh_z = nullptr; h->dh_z_cap = 0;
+    cudaFree(h->d_progress);
+  cudaFree(h->dh_z); h->dh_z = nullptr; h->dh_z_cap = 0;
     A3D_CUDA_OK(cudaMalloc(&h->dh_z, (size_t)n * D * 4));
     h->dh_z_cap = n;
   }

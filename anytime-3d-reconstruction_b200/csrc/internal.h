@@ -66,8 +66,9 @@ int launch_convt_l4_ws(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt,
                        const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
 int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
-                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
-                       cudaStream_t st, int64_t* launches);
+                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, int* progress,
+                       int pace_delta, cudaStream_t st, int64_t* launches);
+size_t convt_l4_sw_progress_bytes();
 int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t n, int fmt, int act,
                          cudaStream_t st, int64_t* launches);
 // Final ConvT(64->1, s2) + sigmoid + mean over K + threshold + TP/FP/FN (+ optional mean grid).

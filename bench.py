@@ -110,7 +110,9 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
-        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+        # started BEFORE the warm-up steps (nvidia-smi needs ~1 s to come up); stop(t0, t1) keeps only the samples whose
+        # own timestamp falls inside the timed region
+        q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         try:
@@ -126,27 +128,34 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
+        """t0, t1: time.time() at the start / end of the timed region."""
+        import datetime
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, reasons, n_all = [], [], [], set(), 0
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for ln in self.lines:
             p = [x.strip() for x in ln.split(',')]
-            if len(p) < 7:
+            if len(p) < 8:
                 continue
             try:
-                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                vals = (float(p[1]), float(p[2]), float(p[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[3:7]):
+            n_all += 1
+            if not (t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
+            sm.append(vals[0]); mx.append(vals[1]); pw.append(vals[2])
+            for nm, v in zip(names, p[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(nm)
-        busy = [s for s, w in zip(sm, pw) if w > 400.0] or sm      # samples taken while the GPU was under load
-        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(pw) if pw else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_median': float(np.median(pw)) if pw else None, 'reasons': sorted(reasons),
+                'samples_in_timed_region': len(sm), 'samples': n_all}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
@@ -551,17 +560,19 @@ def _main(args, saved_stdout):
             ms = float(t.item())
         return ms, acc
 
-    warm = torch.zeros(3, dtype=torch.int64, device=dev)
-    for i in range(args.warmup):
-        step(i, warm)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    warm = torch.zeros(3, dtype=torch.int64, device=dev)
+    for i in range(args.warmup):
+        step(i, warm)
     l0 = dec.launch_count
     last_counts = []
+    t_wall0 = time.time()
     ms, total = timed_steps(args.steps, keep=last_counts)
+    t_wall1 = time.time()
     launches = dec.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     obj_per_step = B_PER_RATE * len(RATES) * world
     value = obj_per_step * args.steps / (ms * 1e-3)
 

@@ -54,7 +54,7 @@ outs = {}
 ok = True
 for impl in (None, 'ws'):
     d = make(impl, 32)
-    d(z)
+    d(torch.from_numpy(z).cuda())     # one chunk through a3d_decode (the numpy path decodes in sub-chunks)
     torch.cuda.synchronize()
     outs[impl] = d.debug_layer(4, n)
     ok &= localise(f'L4 impl={impl or "sw"} vs oracle (n={n})', outs[impl], ref)
