@@ -160,9 +160,12 @@ class Encoder2D:
         return names
 
     def save_weights(self, path: str, save_format: str | None = None) -> None:
-        """``save_format='tf'``: TensorFlow tensor-bundle checkpoint like Keras writes; default: .npz."""
-        if save_format == 'tf':
-            from . import tf_checkpoint
+        """``model.save_weights(path)`` as the reference calls it (nolbo.py:1572-1574, a bare prefix): like Keras, a path
+        without a recognised suffix is written as a TensorFlow tensor-bundle checkpoint (``path.index`` +
+        ``path.data-00000-of-00001`` with the Keras object graph, tf_checkpoint.py); a ``.npz`` path (or
+        ``save_format='npz'``) stores the Keras-order arrays in a numpy archive."""
+        from . import tf_checkpoint
+        if tf_checkpoint.wants_tf_format(path, save_format):
             tf_checkpoint.save_keras_weights(path, self.get_weights(), self._layer_var_names())
             return
         np.savez(path if path.endswith('.npz') else path + '.npz', *self.get_weights())

@@ -5,8 +5,15 @@ src/module/nolbo.py:1568-1592: ``self._decoder.save_weights(os.path.join(save_pa
 
 Pure host code, no TensorFlow needed.  The format is third-party (TensorFlow ``tensor_bundle`` on top of the LevelDB
 table format) and is restated here from its published layout -- PARITY UNPINNED: no TensorFlow is installable in this
-environment, so the reader is tested against the writer below and against hand-built byte strings, not against a file
-written by TensorFlow itself.
+environment, so the reader is tested against the writer below and against hand-built byte strings (snappy blocks,
+multi-shard bundles, string tensors), not against a file written by TensorFlow itself.  tests/golden/make_golden_tf.py
+stores a checkpoint Keras wrote in the TensorFlow fixture; tests/test_golden_tf.py reads it through this module as soon as
+that fixture exists.
+
+Interop with the reference's ``load_weights``: Keras restores TF-format checkpoints through the object graph stored under
+``_CHECKPOINTABLE_OBJECT_GRAPH`` (a serialized ``TrackableObjectGraph`` in a DT_STRING tensor).  ``save_keras_weights``
+writes such a graph (root -> ``layer_with_weights-<i>`` -> variable -> VARIABLE_VALUE attribute with the checkpoint key),
+restated from the TensorFlow protos; like the rest of this file it is unverified against TensorFlow itself.
 
 Layout:
 * ``.index``: LevelDB SSTable.  Blocks of prefix-compressed (key, value) entries followed by a restart array; each block
@@ -31,6 +38,7 @@ _MAGIC = 0xdb4775248b80fb57
 _DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: np.int8, 9: np.int64, 10: np.bool_,
            19: np.float16}
 _DT_BFLOAT16 = 14
+_DT_STRING = 7
 _DTYPE_CODES = {np.dtype(v): k for k, v in _DTYPES.items()}
 _VAR_ORDER = ['kernel', 'bias', 'gamma', 'beta', 'moving_mean', 'moving_variance']
 
@@ -225,9 +233,57 @@ def _parse_entry(buf: bytes) -> dict:
     return e
 
 
-def load_checkpoint(prefix: str, verify: bool = True) -> dict[str, np.ndarray]:
-    """name -> array for every numeric tensor of the checkpoint ``prefix`` (string tensors such as
-    ``_CHECKPOINTABLE_OBJECT_GRAPH`` are skipped)."""
+_warned_crc = []
+
+
+def _crc_matches(raw: bytes, want: int) -> bool:
+    """Masked CRC-32C check of a tensor.  Without liba3d the pure-Python CRC takes ~1 s per MB: large tensors are then
+    accepted unverified, with one warning (this is file I/O; the compute path fails loudly without the library)."""
+    if len(raw) > (4 << 20):
+        try:
+            from . import _capi
+            _capi.lib()
+        except (RuntimeError, OSError, AttributeError):
+            if not _warned_crc:
+                import warnings
+                warnings.warn('liba3d is not built: CRC-32C of large checkpoint tensors is not verified')
+                _warned_crc.append(1)
+            return True
+    return _mask_crc(crc32c(raw)) == want
+
+
+def _parse_string_tensor(raw: bytes, e: dict, key: bytes, verify: bool):
+    """DT_STRING tensor (tensor_bundle.cc WriteStringTensor): [varint64 length] * n, 4-byte masked CRC-32C of the lengths
+    (each taken as a little-endian uint32), then the string bytes.  The entry checksum covers the uint32 lengths, the
+    4-byte length checksum and the bytes.  Returns bytes for a scalar, else a list of bytes."""
+    n = 1
+    for d in e['shape']:
+        n *= d
+    pos, lens = 0, []
+    for _ in range(n):
+        v, pos = _varint(raw, pos)
+        lens.append(v)
+    c = 0
+    for v in lens:
+        c = crc32c(struct.pack('<I', v) if v <= 0xFFFFFFFF else struct.pack('<Q', v), c)
+    cks = raw[pos:pos + 4]
+    if verify and struct.unpack('<I', cks)[0] != _mask_crc(c):
+        raise ValueError(f'{key!r}: string-length checksum mismatch')
+    pos += 4
+    c = crc32c(cks, c)
+    vals = []
+    for v in lens:
+        vals.append(raw[pos:pos + v])
+        c = crc32c(vals[-1], c)
+        pos += v
+    if verify and e['crc32c'] is not None and _mask_crc(c) != e['crc32c']:
+        raise ValueError(f'{key!r}: tensor checksum mismatch')
+    return vals[0] if not e['shape'] else vals
+
+
+def load_checkpoint(prefix: str, verify: bool = True, strings: bool = False) -> dict[str, np.ndarray]:
+    """name -> array for every numeric tensor of the checkpoint ``prefix``; string tensors such as
+    ``_CHECKPOINTABLE_OBJECT_GRAPH`` are skipped unless ``strings`` (they then come back as bytes)."""
     index = read_index(prefix + '.index', verify)
     num_shards = 1
     for fn, _, v in _proto_fields(index.get(b'', b'')):
@@ -247,15 +303,20 @@ def load_checkpoint(prefix: str, verify: bool = True) -> dict[str, np.ndarray]:
             np_dt = None
         elif e['dtype'] in _DTYPES:
             np_dt = np.dtype(_DTYPES[e['dtype']])
+        elif e['dtype'] == _DT_STRING and strings:
+            np_dt = 'string'
         else:
-            continue                                   # DT_STRING etc.
+            continue                                   # DT_STRING (unless asked for), resources, variants
         sid = e['shard_id']
         if sid not in shards:
             shards[sid] = open(f'{prefix}.data-{sid:05d}-of-{num_shards:05d}', 'rb').read()
         raw = shards[sid][e['offset']:e['offset'] + e['size']]
         if len(raw) != e['size']:
             raise ValueError(f'{key!r}: data file is truncated')
-        if verify and e['crc32c'] is not None and _mask_crc(crc32c(raw)) != e['crc32c']:
+        if np_dt == 'string':
+            out[key.decode('utf-8')] = _parse_string_tensor(raw, e, key, verify)
+            continue
+        if verify and e['crc32c'] is not None and not _crc_matches(raw, e['crc32c']):
             raise ValueError(f'{key!r}: tensor checksum mismatch')
         if np_dt is None:
             a = (np.frombuffer(raw, '<u2').astype(np.uint32) << 16).view(np.float32)
@@ -320,12 +381,77 @@ def _build_block(entries: list[tuple[bytes, bytes]], restart_interval: int = 16)
     return bytes(out)
 
 
-def save_checkpoint(prefix: str, tensors: dict[str, np.ndarray], block_entries: int = 64) -> None:
+def _string_tensor_bytes(val: bytes) -> tuple[bytes, int]:
+    """Scalar DT_STRING payload and its (unmasked) entry checksum, see _parse_string_tensor."""
+    ln = struct.pack('<I', len(val))
+    c = crc32c(ln)
+    cks = struct.pack('<I', _mask_crc(c))
+    c = crc32c(val, crc32c(cks, c))
+    return _put_varint(len(val)) + cks + val, c
+
+
+def object_graph_proto(layer_var_names: list[list[str]]) -> bytes:
+    """Serialized ``TrackableObjectGraph`` of a Keras model whose weighted layers own the variables ``layer_var_names``:
+    node 0 = the model with children ``layer_with_weights-<i>``; each layer node has one child per variable; each variable
+    node carries the attribute (name 'VARIABLE_VALUE', full_name, checkpoint_key).
+    TrackableObjectGraph{1: nodes}; TrackableObject{1: children{1: node_id, 2: local_name}, 2: attributes{1: name,
+    2: full_name, 3: checkpoint_key}}."""
+    nodes = [[]]                                   # list of (children | attribute) byte strings per node
+    root = []
+    for i, names in enumerate(layer_var_names):
+        layer_id = len(nodes)
+        nodes.append([])
+        root.append(_proto_bytes(1, _proto_varint(1, layer_id) + _proto_bytes(2, f'layer_with_weights-{i}'.encode())))
+        for n in names:
+            var_id = len(nodes)
+            key = f'layer_with_weights-{i}/{n}/.ATTRIBUTES/VARIABLE_VALUE'
+            nodes.append([_proto_bytes(2, _proto_bytes(1, b'VARIABLE_VALUE') + _proto_bytes(2, f'layer_{i}/{n}:0'.encode()) +
+                                       _proto_bytes(3, key.encode()))])
+            nodes[layer_id].append(_proto_bytes(1, _proto_varint(1, var_id) + _proto_bytes(2, n.encode())))
+    nodes[0] = root
+    return b''.join(_proto_bytes(1, b''.join(parts)) for parts in nodes)
+
+
+def parse_object_graph(buf: bytes) -> list[dict]:
+    """Inverse of object_graph_proto (also reads TensorFlow's own): one dict per node with `children` {name: node id} and
+    `attributes` [(name, full_name, checkpoint_key)]."""
+    out = []
+    for fn, _, node in _proto_fields(buf):
+        if fn != 1:
+            continue
+        d = {'children': {}, 'attributes': []}
+        for f2, _, v in _proto_fields(node):
+            if f2 == 1:
+                nid, name = 0, ''
+                for f3, _, v3 in _proto_fields(v):
+                    if f3 == 1:
+                        nid = v3
+                    elif f3 == 2:
+                        name = v3.decode()
+                d['children'][name] = nid
+            elif f2 == 2:
+                a = {1: b'', 2: b'', 3: b''}
+                for f3, _, v3 in _proto_fields(v):
+                    if f3 in a:
+                        a[f3] = v3
+                d['attributes'].append((a[1].decode(), a[2].decode(), a[3].decode()))
+        out.append(d)
+    return out
+
+
+def save_checkpoint(prefix: str, tensors: dict, block_entries: int = 64) -> None:
     """Write ``tensors`` as a single-shard tensor bundle (uncompressed blocks) readable by ``load_checkpoint`` and laid
-    out like TensorFlow's BundleWriter output."""
+    out like TensorFlow's BundleWriter output.  ``bytes`` values are written as scalar DT_STRING tensors."""
     data = bytearray()
     items = [(b'', _proto_varint(1, 1) + _proto_bytes(3, _proto_varint(1, 1)))]   # num_shards = 1, version.producer = 1
     for name in sorted(tensors):
+        if isinstance(tensors[name], (bytes, bytearray)):
+            raw, c = _string_tensor_bytes(bytes(tensors[name]))
+            entry = (_proto_varint(1, _DT_STRING) + _proto_bytes(2, b'') + (_proto_varint(4, len(data)) if len(data) else b'') +
+                     _proto_varint(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack('<I', _mask_crc(c)))
+            items.append((name.encode('utf-8'), entry))
+            data += raw
+            continue
         a = np.asarray(tensors[name])
         code = _DTYPE_CODES.get(a.dtype)
         if code is None:
@@ -364,9 +490,27 @@ def save_checkpoint(prefix: str, tensors: dict[str, np.ndarray], block_entries: 
 
 def save_keras_weights(prefix: str, weights: list[np.ndarray], layer_var_names: list[list[str]]) -> None:
     """Write a Keras-style object-graph checkpoint: ``layer_var_names[i]`` lists the variable names of weighted layer
-    ``i`` in get_weights() order (e.g. [['kernel', 'bias'], ['gamma', 'beta', 'moving_mean', 'moving_variance'], ...])."""
+    ``i`` in get_weights() order (e.g. [['kernel', 'bias'], ['gamma', 'beta', 'moving_mean', 'moving_variance'], ...]);
+    the ``_CHECKPOINTABLE_OBJECT_GRAPH`` entry Keras' own ``load_weights`` restores through is written too."""
     tensors, it = {}, iter(weights)
     for i, names in enumerate(layer_var_names):
         for n in names:
             tensors[f'layer_with_weights-{i}/{n}/.ATTRIBUTES/VARIABLE_VALUE'] = np.asarray(next(it), np.float32)
+    tensors['_CHECKPOINTABLE_OBJECT_GRAPH'] = object_graph_proto(layer_var_names)
     save_checkpoint(prefix, tensors)
+
+
+def wants_tf_format(path: str, save_format) -> bool:
+    """Keras' rule for ``save_weights(path, save_format=None)``: '.h5' / '.hdf5' / '.keras' suffixes mean HDF5, anything
+    else the TensorFlow checkpoint format (nolbo.py:1572-1574 passes a bare prefix).  '.npz' keeps this package's own
+    archive; HDF5 is not implemented."""
+    if save_format is not None:
+        if save_format in ('tf', 'tensorflow'):
+            return True
+        if save_format == 'npz':
+            return False
+        raise NotImplementedError(f"save_format={save_format!r}: only 'tf' and 'npz' are implemented")
+    low = path.lower()
+    if low.endswith(('.h5', '.hdf5', '.keras')):
+        raise NotImplementedError('HDF5 weight files are not implemented; use a checkpoint prefix or a .npz path')
+    return not low.endswith('.npz')

@@ -243,11 +243,14 @@ def test_tf_checkpoint_weight_io_round_trip(a3d_mod, tmp_path):
     z = dr.round_bf16(np.random.default_rng(2).standard_normal((2, 16)).astype(np.float32))
     want = dec(z)
     prefix = str(tmp_path / 'weights' / 'decoder')
-    dec.save_weights(prefix, save_format='tf')
+    dec.save_weights(prefix)            # bare prefix, like nolbo.py:1572-1574: Keras' default is the TF checkpoint format
     assert os.path.exists(prefix + '.index') and os.path.exists(prefix + '.data-00000-of-00001')
     dec2 = a3d_mod.decoder3D(a3d_mod.presets.PASCAL_DECODER, max_chunk=32)
     dec2.load_weights(prefix)
     assert all(np.array_equal(a, b) for a, b in zip(dec2.get_weights(), dws))
+    assert np.array_equal(dec2(z), want)
+    dec.save_weights(prefix + '.npz')   # explicit numpy archive
+    dec2.load_weights(prefix + '.npz')
     assert np.array_equal(dec2(z), want)
     dec.close(); dec2.close()
     layers = er.layer_list()

@@ -108,3 +108,101 @@ def test_keras_order_is_numeric_by_layer_then_variable(tmp_path):
     assert len(back) == 27 and all(np.array_equal(a, b) for a, b in zip(back, ws))
     with pytest.raises(ValueError, match='not a Keras'):
         tc.keras_weight_list({'foo': np.zeros(1)})
+
+
+def _literal_snappy(raw: bytes) -> bytes:
+    """A valid snappy stream made of literals (<= 60 bytes each) plus one back-reference copy when the data allows it."""
+    out = bytearray(tc._put_varint(len(raw)))
+    pos = 0
+    while pos < len(raw):
+        if pos >= 8 and raw[pos:pos + 4] == raw[pos - 4:pos] and pos + 4 <= len(raw):      # copy(offset 4, len 4)
+            out += bytes([((4 - 4) << 2) | 1, 4])
+            pos += 4
+            continue
+        n = min(60, len(raw) - pos)
+        out += bytes([(n - 1) << 2]) + raw[pos:pos + n]
+        pos += n
+    return bytes(out)
+
+
+def _table(blocks, compress):
+    """LevelDB table with one data block per entry list; `compress` -> snappy (type 1) data blocks."""
+    table = bytearray()
+    handles = []
+    for entries in blocks:
+        blk = tc._build_block(entries)
+        body, ctype = (_literal_snappy(blk), b'\x01') if compress else (blk, b'\x00')
+        handles.append((entries[-1][0], tc._put_varint(len(table)) + tc._put_varint(len(body))))
+        table += body + ctype + struct.pack('<I', tc._mask_crc(tc.crc32c(body + ctype)))
+    off = len(table)
+    iblk = tc._build_block(handles, 1)
+    table += iblk + b'\x00' + struct.pack('<I', tc._mask_crc(tc.crc32c(iblk + b'\x00')))
+    footer = tc._put_varint(off) + tc._put_varint(len(iblk)) + tc._put_varint(off) + tc._put_varint(len(iblk))
+    table += footer + b'\x00' * (40 - len(footer)) + struct.pack('<Q', 0xdb4775248b80fb57)
+    return bytes(table)
+
+
+def test_hand_assembled_bundle_snappy_multi_shard_and_object_graph(tmp_path):
+    """What a TensorFlow-written Keras checkpoint can contain beyond this package's own writer: snappy-compressed index
+    blocks, tensors spread over two data shards, and the _CHECKPOINTABLE_OBJECT_GRAPH string tensor."""
+    rng = np.random.default_rng(4)
+    names = [['kernel', 'bias'], ['gamma', 'beta', 'moving_mean', 'moving_variance'], ['kernel']]
+    ws = [rng.standard_normal(s).astype(np.float32) for s in [(3, 4), (4,), (4,), (4,), (4,), (4,), (2, 2, 2, 5, 4)]]
+    graph = tc.object_graph_proto(names)
+    shards = [bytearray(), bytearray()]
+    entries = []
+    it = iter(ws)
+    for i, vs in enumerate(names):
+        for v in vs:
+            a = next(it)
+            raw = a.tobytes()
+            sid = (i + len(v)) & 1
+            shape = b''.join(tc._proto_bytes(2, tc._proto_varint(1, int(d))) for d in a.shape)
+            e = (tc._proto_varint(1, 1) + tc._proto_bytes(2, shape) + (tc._proto_varint(3, sid) if sid else b'') +
+                 (tc._proto_varint(4, len(shards[sid])) if len(shards[sid]) else b'') + tc._proto_varint(5, len(raw)) +
+                 tc._put_varint((6 << 3) | 5) + struct.pack('<I', tc._mask_crc(tc.crc32c(raw))))
+            entries.append((f'layer_with_weights-{i}/{v}/.ATTRIBUTES/VARIABLE_VALUE'.encode(), e))
+            shards[sid] += raw
+    sraw, c = tc._string_tensor_bytes(graph)
+    entries.append((b'_CHECKPOINTABLE_OBJECT_GRAPH', tc._proto_varint(1, 7) + tc._proto_bytes(2, b'') + tc._proto_varint(3, 1) +
+                    tc._proto_varint(4, len(shards[1])) + tc._proto_varint(5, len(sraw)) + tc._put_varint((6 << 3) | 5) +
+                    struct.pack('<I', tc._mask_crc(c))))
+    shards[1] += sraw
+    header = (b'', tc._proto_varint(1, 2) + tc._proto_bytes(3, tc._proto_varint(1, 1)))      # num_shards = 2
+    entries = sorted([header] + entries)
+    prefix = str(tmp_path / 'decoder')
+    open(prefix + '.index', 'wb').write(_table([entries[:4], entries[4:]], compress=True))
+    for i in range(2):
+        open(f'{prefix}.data-{i:05d}-of-00002', 'wb').write(bytes(shards[i]))
+    back = tc.load_keras_weights(prefix)
+    assert len(back) == 7 and all(np.array_equal(a, b) for a, b in zip(back, ws))
+    got = tc.load_checkpoint(prefix, strings=True)
+    nodes = tc.parse_object_graph(got['_CHECKPOINTABLE_OBJECT_GRAPH'])
+    assert list(nodes[0]['children']) == ['layer_with_weights-0', 'layer_with_weights-1', 'layer_with_weights-2']
+    bn = nodes[nodes[0]['children']['layer_with_weights-1']]
+    assert list(bn['children']) == names[1]
+    var = nodes[bn['children']['moving_variance']]
+    assert var['attributes'] == [('VARIABLE_VALUE', 'layer_1/moving_variance:0',
+                                  'layer_with_weights-1/moving_variance/.ATTRIBUTES/VARIABLE_VALUE')]
+    # a corrupted string tensor is detected
+    bad = bytearray(shards[1]); bad[-3] ^= 0x55
+    open(f'{prefix}.data-00001-of-00002', 'wb').write(bytes(bad))
+    with pytest.raises(ValueError, match='checksum'):
+        tc.load_checkpoint(prefix, strings=True)
+
+
+def test_writer_emits_the_object_graph_and_keras_format_rule(tmp_path):
+    names = [['kernel', 'bias'], ['kernel']]
+    ws = [np.ones((2, 3), np.float32), np.zeros(3, np.float32), np.full((3, 1), 2.0, np.float32)]
+    prefix = str(tmp_path / 'm')
+    tc.save_keras_weights(prefix, ws, names)
+    got = tc.load_checkpoint(prefix, strings=True)
+    assert tc.parse_object_graph(got['_CHECKPOINTABLE_OBJECT_GRAPH'])[0]['children'] == {'layer_with_weights-0': 1,
+                                                                                          'layer_with_weights-1': 4}
+    assert all(np.array_equal(a, b) for a, b in zip(tc.load_keras_weights(prefix), ws))
+    # Keras: no recognised suffix -> TensorFlow checkpoint format (nolbo.py:1572-1574 passes a bare prefix)
+    assert tc.wants_tf_format('weights/decoder', None) and tc.wants_tf_format('x.ckpt', None)
+    assert not tc.wants_tf_format('weights/decoder.npz', None) and not tc.wants_tf_format('d', 'npz')
+    assert tc.wants_tf_format('d.npz', 'tf')
+    with pytest.raises(NotImplementedError):
+        tc.wants_tf_format('decoder.h5', None)
