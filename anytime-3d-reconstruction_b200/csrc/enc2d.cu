@@ -80,6 +80,7 @@ struct a3d_enc2d {
 namespace {
 
 int check(const a3d_enc2d* h) {
+  cudaGetLastError();   // drop a stale non-sticky error left by another runtime user (see check_handle in handle.cu)
   if (!h) { set_error("null encoder handle"); return A3D_ERR_INVALID; }
   if (h->sticky) { set_error("encoder handle is in a sticky CUDA error state (%d)", h->sticky); return h->sticky; }
   return A3D_OK;

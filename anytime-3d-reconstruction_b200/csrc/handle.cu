@@ -868,6 +868,7 @@ int a3d_anytime_eval_host(a3d_handle* h, const float* z, const float* mask, cons
   A3D_CUDA_OK(cudaMemcpyAsync(h->st_mask, mask, (size_t)B * D * 4, cudaMemcpyHostToDevice, st));
   if (mu_table) A3D_CUDA_OK(cudaMemcpyAsync(h->st_mu, mu_table, (size_t)C * D * 4, cudaMemcpyHostToDevice, st));
   A3D_CUDA_OK(cudaMemcpyAsync(h->st_bits, target_bits, (size_t)B * (A3D_VOXELS / 8), cudaMemcpyHostToDevice, st));
+  cudaGetLastError();   // see a3d_decode_host
   if ((rc = a3d_impute(h, h->st_z, h->st_mask, h->st_mu, C, B, K, seed, obj_offset, fill_mode, h->st_zout, nullptr, st)))
     return rc;
   if ((rc = a3d_anytime_eval(h, h->st_zout, B, K, h->st_bits, thr, reinterpret_cast<int64_t*>(h->st_counts),
@@ -926,8 +927,7 @@ int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_hos
     }
   }
   if (n > h->dh_z_cap) {
-    cudaFree(h->d_progress);
-  cudaFree(h->dh_z); h->dh_z = nullptr; h->dh_z_cap = 0;
+    cudaFree(h->dh_z); h->dh_z = nullptr; h->dh_z_cap = 0;
     A3D_CUDA_OK(cudaMalloc(&h->dh_z, (size_t)n * D * 4));
     h->dh_z_cap = n;
   }
@@ -944,6 +944,7 @@ int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_hos
   const size_t per = out_dtype == A3D_OUT_F32 ? (size_t)A3D_VOXELS * 4 : out_dtype == A3D_OUT_F16 ? (size_t)A3D_VOXELS * 2
                                                                                                : (size_t)A3D_VOXELS / 8;
   A3D_CUDA_OK(cudaMemcpyAsync(h->dh_z, z_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, cs));
+  cudaGetLastError();   // a copy from pageable memory can leave a benign error behind (see check_handle): not a launch failure
   const int64_t nsub = (n + sub - 1) / sub;
   auto compute = [&](int64_t i) -> int {
     const int b = (int)(i & 1);
@@ -971,9 +972,11 @@ int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_hos
     A3D_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + (size_t)off * per, src, (size_t)nc * per,
                                 cudaMemcpyDeviceToHost, ps));
     A3D_CUDA_OK(cudaEventRecord(h->dh_free[b], ps));
+    cudaGetLastError();
   }
   cudaError_t e = cudaStreamSynchronize(ps);
   if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+  cudaGetLastError();   // the driver's staging path of a pageable D2H copy can leave a benign error in the last-error slot
   if (e != cudaSuccess) {
     set_error("a3d_decode_host: %s", cudaGetErrorString(e));
     h->sticky = A3D_ERR_CUDA;

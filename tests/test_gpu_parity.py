@@ -427,6 +427,7 @@ def test_pascal_path_config3(a3d_mod, decoders, weights):
     r = a3d_mod.anytime_eval(dec, None, None, None, tgt, z_completed=z[:, None, :], return_grid=True)
     ref_mp, ref_cnt = ar.anytime_eval(dr.PASCAL_DECODER, ws, z[:, None, :], tgt)
     mp = r['mean_prob'].cpu().numpy()
+    assert np.isfinite(mp).all()
     nflip = int(((mp >= 0.5) != (ref_mp >= 0.5)).sum())
     assert np.abs(mp - ref_mp).max() < PROB_TOL and nflip / mp.size < FLIP_TOL
     assert np.abs(r['counts'].cpu().numpy() - ref_cnt).sum() <= 2 * nflip
