@@ -4,6 +4,7 @@
 //   pack     -- fp32 {0,1} targets (loader layout, pascal3D.py:149-152) -> 1 bit / voxel
 #include "internal.h"
 #include "philox.cuh"
+#include "ptx.cuh"
 
 namespace a3d {
 namespace {
@@ -20,6 +21,7 @@ impute_kernel(const float* __restrict__ z, const float* __restrict__ mask, const
   __shared__ int cstar_s;
   const int64_t b = blockIdx.x;
   const uint64_t obj = obj_offset + (uint64_t)b;
+  ptx::pdl_sync();     // first kernel of a call's chain: lets the Dense kernel's launch overlap this one
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float m = mask[b * D + d];
     float v = z[b * D + d] * m;                       // nolbo.py:1477
@@ -320,8 +322,8 @@ int launch_impute(const float* z, const float* mask, const float* mu, int C, int
     set_error("a3d_impute: latent_dim %d / %d categories need %zu bytes of shared memory (limit 48 KB)", D, C, smem);
     return A3D_ERR_INVALID;
   }
-  impute_kernel<<<(unsigned)B, 128, smem, st>>>(z, mask, mu, C, K, D, seed, obj_offset, fill, z_out, cstar);
-  A3D_CUDA_OK(cudaGetLastError());
+  A3D_CUDA_OK(launch_chain(impute_kernel, dim3((unsigned)B), dim3(128), smem, st, 1, z, mask, mu, C, K, D, seed, obj_offset,
+                           fill, z_out, cstar));
   if (launches) ++*launches;
   return A3D_OK;
 }

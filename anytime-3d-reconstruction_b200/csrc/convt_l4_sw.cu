@@ -201,6 +201,8 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp != 0 || lane != 0) ptx::pdl_sync();   // the producer lane first puts the resident weights in flight
+
   if (warp == 0) {
     // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
@@ -230,6 +232,9 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 #pragma unroll
         for (int j = 0; j < W_BYTES / 32768; ++j)
           ptx::tma_load_2d_2sm(smem_w + j * 32768, &tmap_wgt, w_full, 0, wrow0 + j * 256);
+        // the weights are constants: under programmatic dependent launch the first 128 KB per CTA are in flight while
+        // the previous layer is still draining; its output is only touched after pdl_sync()
+        if (w_loads == 0) ptx::pdl_sync();
         ++w_loads;
         for (int k = 0; k < S.count; ++k) {
           const int t = seg_item(S, k);
@@ -257,6 +262,7 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
         }
       }
+      if (w_loads == 0) ptx::pdl_sync();   // (a cluster without work still takes part in the launch chain)
       // done: nobody may wait for this cluster any more, and its poller can stop
       if (pace_on) {
         st_relaxed_gpu(progress + cluster_id * kPaceStride, 0x7fffffff);
@@ -505,9 +511,8 @@ int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt,
   if (progress) A3D_CUDA_OK(cudaMemsetAsync(progress, 0, kProgressInts * sizeof(int), st));
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kern<<<2 * n_clusters, kThreads, SMEM_BYTES, st>>>(tmap_act, tmap_wgt, reinterpret_cast<uint16_t*>(out), scale,
-                                                       shift, n_blocks, (int)n_alloc, progress, pace_delta);
-    A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(kern, dim3(2 * n_clusters), dim3(kThreads), SMEM_BYTES, st, 1, tmap_act, tmap_wgt,
+                             reinterpret_cast<uint16_t*>(out), scale, shift, n_blocks, (int)n_alloc, progress, pace_delta));
     return A3D_OK;
   };
   int rc;

@@ -124,6 +124,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   if constexpr (PAIR == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();     // the input activations are the previous kernel's output
 
   if (warp == kWarpTma) {
     // ===================================================== TMA producer (one per CTA)
@@ -361,20 +362,9 @@ int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fm
   const CUtensorMap& tw = (PAIR == 2) ? L.tmap_wgt64 : L.tmap_wgt;
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_cl * PAIR);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    A3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, L.tmap_act, tw, reinterpret_cast<uint16_t*>(out),
-                                   (const float*)L.scale, (const float*)L.shift, n_blocks, (int)n_alloc));
+    A3D_CUDA_OK(launch_chain(kern, dim3(n_cl * PAIR), dim3(kThreads), C::SMEM_BYTES, st, PAIR, L.tmap_act, tw,
+                             reinterpret_cast<uint16_t*>(out), (const float*)L.scale, (const float*)L.shift, n_blocks,
+                             (int)n_alloc));
     return A3D_OK;
   };
   if (fmt == A3D_DTYPE_F16) {
@@ -402,16 +392,35 @@ size_t convt_tc_smem_bytes(int cin, int cout, int win) {
   return 0;
 }
 
+// PAIR = 2 shares every weight tile between two decode blocks but needs an even number of blocks and halves the number
+// of schedulable workers; for small calls (the reference's 32- and 72-latent decoder calls) the single-CTA kernel wins
+// whenever it saves a scheduling round.  `slowdown` = measured unit time of PAIR = 1 relative to PAIR = 2 per row of work.
+template <class C2, class C1>
+bool prefer_single(int64_t n, int num_sms, float slowdown) {
+  const int nb = (int)((n + C2::NT - 1) / C2::NT);
+  auto rounds = [](int units, int workers) { return (units + workers - 1) / workers; };
+  int w2 = num_sms / 2, w1 = num_sms;
+  if (w2 > C2::NPAR) w2 -= w2 % C2::NPAR;
+  if (w1 > C1::NPAR) w1 -= w1 % C1::NPAR;
+  const int u2 = ((nb + 1) / 2) * C2::WIN * C2::WIN * C2::NPAR, u1 = nb * C1::WIN * C1::WIN * C1::NPAR;
+  return rounds(u1, w1 < 1 ? 1 : w1) * slowdown < (float)rounds(u2, w2 < 1 ? 1 : w2);
+}
+
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches) {
-  static const int pair = (getenv("A3D_CONV_PAIR") && atoi(getenv("A3D_CONV_PAIR")) == 1) ? 1 : 2;
+  static const int pair_env = getenv("A3D_CONV_PAIR") ? atoi(getenv("A3D_CONV_PAIR")) : 0;   // 1 / 2 force a variant
   int rc;
-  if (L.cin == 512 && L.cout == 256 && L.win == 4)
-    rc = pair == 2 ? launch_cfg<Cfg<512, 256, 4, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st)
-                   : launch_cfg<Cfg<512, 256, 4, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
-  else if (L.cin == 256 && L.cout == 128 && L.win == 8)
-    rc = pair == 2 ? launch_cfg<Cfg<256, 128, 8, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st)
-                   : launch_cfg<Cfg<256, 128, 8, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  if (L.cin == 512 && L.cout == 256 && L.win == 4) {
+    using C2 = Cfg<512, 256, 4, 2>;
+    using C1 = Cfg<512, 256, 4, 1>;
+    const bool single = pair_env == 1 || (pair_env != 2 && prefer_single<C2, C1>(n, num_sms, 1.3f));
+    rc = single ? launch_cfg<C1>(L, out, n, n_alloc, fmt, act, num_sms, st) : launch_cfg<C2>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  } else if (L.cin == 256 && L.cout == 128 && L.win == 8) {
+    using C2 = Cfg<256, 128, 8, 2>;
+    using C1 = Cfg<256, 128, 8, 1>;
+    const bool single = pair_env == 1 || (pair_env != 2 && prefer_single<C2, C1>(n, num_sms, 1.07f));
+    rc = single ? launch_cfg<C1>(L, out, n, n_alloc, fmt, act, num_sms, st) : launch_cfg<C2>(L, out, n, n_alloc, fmt, act, num_sms, st);
+  }
   else if (L.cin == 128 && L.cout == 64 && L.win == 16)
     rc = launch_cfg<Cfg<128, 64, 16, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   else {

@@ -71,6 +71,7 @@ gemm_l1_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();     // a0 is the previous kernel's output
 
   if (warp == 0) {
     if (lane == 0) {   // ===================================================== TMA producer
@@ -188,9 +189,8 @@ int launch_gemm_l1(const CUtensorMap& tmap_a0, const CUtensorMap& tmap_mt, void*
   const int grid = total < num_sms ? total : num_sms;
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap_a0, tmap_mt, reinterpret_cast<uint16_t*>(a1), scale, shift, m_tiles,
-                                             (int)n_alloc);
-    A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), SMEM_BYTES, st, 1, tmap_a0, tmap_mt,
+                             reinterpret_cast<uint16_t*>(a1), scale, shift, m_tiles, (int)n_alloc));
     return A3D_OK;
   };
   int rc;

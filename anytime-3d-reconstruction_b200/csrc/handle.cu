@@ -41,6 +41,11 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("A3D_PDL") && atoi(getenv("A3D_PDL")) == 0);
+  return on;
+}
+
 uint16_t cvt16(float v, int fmt) {
   if (fmt == A3D_DTYPE_F16) {
     __half h = __float2half_rn(v);

@@ -24,6 +24,38 @@ void set_error(const char* fmt, ...);
 
 constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default epsilon
 
+// Launch a kernel of the decoder chain with programmatic stream serialization (see ptx::pdl_sync): the kernel's
+// prologue overlaps the tail of the previous kernel in the stream.  A3D_PDL=0 turns the attribute off (plain
+// stream-ordered launches; griddepcontrol.* are then no-ops).  `cluster` > 1 adds a run-time cluster dimension (kernels
+// with a compile-time __cluster_dims__ pass 1).
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // host helpers shared by handle.cu (decoder) and enc2d.cu (image encoder)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -22,6 +22,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the decoder chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_chain in
+// internal.h): its CTAs may become resident and run their prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// constant loads) while the previous kernel of the stream is still draining.  pdl_sync() is the point after which the
+// previous kernel's results may be read and global memory may be written: griddepcontrol.wait returns once the
+// previous grid has completed and flushed (immediately when the kernel was launched without the attribute), and
+// launch_dependents then lets the NEXT kernel of the chain start its own prologue.  Every thread of every chain kernel
+// executes it exactly once, so completion of a kernel implies completion of all its predecessors.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

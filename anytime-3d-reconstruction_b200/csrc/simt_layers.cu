@@ -3,6 +3,7 @@
 // ConvT used only as an on-device diagnostic for the tcgen05 kernel (A3D_IMPL_SIMT).
 #include "cvt.cuh"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace a3d {
 namespace {
@@ -16,6 +17,7 @@ __global__ void dense_kernel(const float* __restrict__ z, int D, const float* __
                              const float* __restrict__ shift, uint16_t* __restrict__ a0, int units, int act) {
   extern __shared__ float zs[];
   const int64_t n = blockIdx.x;
+  ptx::pdl_sync();     // z may be the imputation kernel's output; a0 was read by the previous call's chain
   for (int i = threadIdx.x; i < D; i += blockDim.x) zs[i] = z[n * D + i];
   __syncthreads();
   for (int j = threadIdx.x; j < units; j += blockDim.x) {
@@ -144,11 +146,13 @@ int launch_dense_l1(const float* z, int64_t n, int D, const float* wd, const flo
   constexpr int NB = 16;
   const int blocks1 = (int)((n + NB - 1) / NB);
   if (fmt == A3D_DTYPE_F16) {
-    dense_kernel<A3D_DTYPE_F16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
+    A3D_CUDA_OK(launch_chain(dense_kernel<A3D_DTYPE_F16>, dim3((unsigned)n), dim3(256), D * sizeof(float), st, 1, z, D, wd, bd,
+                             s0, h0, (uint16_t*)a0, 512, act));
     if (do_s1) convt_s1_kernel<A3D_DTYPE_F16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
                                                                (uint16_t*)a1, n, act);
   } else {
-    dense_kernel<A3D_DTYPE_BF16><<<(unsigned)n, 256, D * sizeof(float), st>>>(z, D, wd, bd, s0, h0, (uint16_t*)a0, 512, act);
+    A3D_CUDA_OK(launch_chain(dense_kernel<A3D_DTYPE_BF16>, dim3((unsigned)n), dim3(256), D * sizeof(float), st, 1, z, D, wd, bd,
+                             s0, h0, (uint16_t*)a0, 512, act));
     if (do_s1) convt_s1_kernel<A3D_DTYPE_BF16, NB><<<blocks1, 256, 0, st>>>((const uint16_t*)a0, (const uint16_t*)w1_tco, s1, h1,
                                                                 (uint16_t*)a1, n, act);
   }

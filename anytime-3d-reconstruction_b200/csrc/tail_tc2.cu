@@ -110,6 +110,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();     // a4 is the previous kernel's output; counts / loss were zeroed earlier in the stream
 
   if (warp == 0) {
     // ===================================================== TMA producer (converged warp, elected-lane issue)
@@ -427,8 +428,8 @@ int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, i
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    kern<<<grid, kThreads, kSmem, st>>>(tmap_a4p, tmap_w5p, B, K, target_bits, thr, counts, mean_prob, gamma, loss);
-    A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), kSmem, st, 1, tmap_a4p, tmap_w5p, B, K, target_bits, thr,
+                             counts, mean_prob, gamma, loss));
     return A3D_OK;
   };
   // sigmoid mode: 1 = tanh form for the counts-only path, 2 = exp form whenever probabilities or the loss are emitted

@@ -4,7 +4,7 @@
   * anytime_eval at B=1 x K=32 and B=32 x K=1 (counts only);
   * decoder(z) numpy -> numpy through a3d_decode_host at B=72 / 4096, fp32 / fp16 / bit outputs, pinned output buffer,
     against the measured pinned D2H rate of the box.
-Usage: python tests/tools/bench_small.py [--big 4096]"""
+Usage: python tests/tools/bench_small.py [--big 4096] [--small-only]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
@@ -55,6 +55,9 @@ for B, K in ((1, 32), (32, 1)):
     bits = torch.zeros((B, 32768), dtype=torch.uint8, device='cuda')
     t = timed(lambda: a3d.anytime_eval(dec, None, None, None, bits, z_completed=zc))
     print(f'anytime_eval B={B} K={K} (counts only, device in/out): {t:.1f} us per call', flush=True)
+
+if '--small-only' in sys.argv:
+    sys.exit(0)
 
 # pinned D2H rate of this box
 src = torch.empty(1 << 28, dtype=torch.uint8, device='cuda')
