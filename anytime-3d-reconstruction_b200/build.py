@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 LIB = os.path.join(HERE, 'liba3d.so')
-SOURCES = ['handle.cu', 'convt_tc.cu', 'convt_l4_ws.cu', 'convt_l4_sw.cu', 'gemm_l1.cu', 'simt_layers.cu', 'tail.cu', 'tail_tc.cu', 'tail_tc2.cu', 'aux_kernels.cu',
+SOURCES = ['handle.cu', 'convt_tc.cu', 'convt_l4_sw.cu', 'gemm_l1.cu', 'simt_layers.cu', 'tail.cu', 'tail_hcol.cu', 'aux_kernels.cu',
            'conv2d_tc.cu', 'conv2d_pair.cu', 'conv2d_first_tc.cu', 'enc2d_kernels.cu', 'enc2d.cu',
            'conv3d_tc.cu', 'enc3d.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

@@ -1,8 +1,8 @@
 // 128 -> 64 stride-2 transposed conv (58.6 % of the decoder FLOPs, conv3DDec, autoencoder3D.py:41-54) as a
 // weight-stationary 2-CTA tcgen05 kernel that SWEEPS ALONG W and resolves the w taps inside a ring of TMEM accumulators.
 //
-// Why: in convt_l4_ws.cu (round 1) the delta_w = -1 / +1 taps were separate N = 64 MMAs over w-shifted views of the
-// activation tile.  An N = 64 MMA reads 5 KB of shared-memory operands per 32 tensor clocks, more than the 128 B/clk
+// Why: in the round-1 kernel (h-sweep, removed; profiles/r01_l4_ws2cta_ncu_full.txt) the delta_w = -1 / +1 taps were
+// separate N = 64 MMAs over w-shifted views of the activation tile.  An N = 64 MMA reads 5 KB of shared-memory operands per 32 tensor clocks, more than the 128 B/clk
 // the port delivers: that kernel sat at 81 % tensor-active, port bound.  Here every MMA is M = 256 (CTA pair), N = 256:
 // 8 KB of operands per 128 tensor clocks per CTA = half the port.
 //
@@ -23,7 +23,7 @@
 //     MMAs accumulate and no MMA ever has to mix fresh and live columns.
 //   * Items (decode-block pair, d) are 16 steps; consecutive items of a cluster start alternately in phase A and C, so
 //     the first window of an item never touches a slot the previous item's last drain still owns.
-// Everything else follows convt_l4_ws.cu: clusters own one (pd, ph) output-parity class for the whole launch (128 KB
+// Otherwise: clusters own one (pd, ph) output-parity class for the whole launch (128 KB
 // of weights per CTA resident in shared memory), activation tiles stream through a 4-stage TMA ring, the leader CTA's
 // MMA warp drives both SMs, 8 epilogue warps per CTA (folded BN + activation + 16-bit pack + staged 64-byte stores).
 #include <cstdlib>

@@ -1,6 +1,6 @@
 // Stride-2 transposed 3-D convolution (k = 4, padding 'same') + folded BatchNorm + activation as a tcgen05
 // implicit GEMM for sm_100a.  Replaces conv3DDec(), /root/reference/src/net_core/autoencoder3D.py:41-54, for the
-// stride-2 hidden layers (512->256, 256->128; the 128->64 layer normally runs in convt_l4_ws.cu).
+// stride-2 hidden layers (512->256, 256->128; the 128->64 layer normally runs in convt_l4_sw.cu).
 //
 // Formulation.  Output voxel o = 2j + p (p = parity per axis) receives input voxels j + delta with tap
 // t = p + 1 - 2*delta:   p = 0: delta in {-1, 0} (taps 3, 1);   p = 1: delta in {0, +1} (taps 2, 0).
@@ -18,7 +18,7 @@
 // decode blocks as ONE tcgen05 cta_group::2 MMA of M = 256.  They share every weight tile: each CTA loads and holds
 // only its N-half (contiguous row ranges of the repacked weights), which halves the TMA weight writes and the
 // B-operand reads -- these layers are bound by shared-memory bandwidth (MMA operand reads + TMA writes), not by the
-// tensor pipe.  PAIR = 1 keeps the single-CTA path (A3D_CONV_PAIR=1, and the 128->64 layer with A3D_L4_IMPL=generic).
+// tensor pipe.  PAIR = 1 keeps the single-CTA path (small calls, A3D_CONV_PAIR=1, and the 128->64 layer with A3D_L4_IMPL=generic).
 //
 // Roles (384 threads): warps 0..7 = epilogue, warp 8 = TMEM allocator, warp 10 = TMA producer, warp 11 = MMA issuer
 // (converged warp; only tcgen05.mma / commit are predicated on an elected lane, so descriptors stay in uniform
@@ -60,7 +60,7 @@ struct Cfg {
   static_assert(BROWS % BSLOT_ROWS == 0, "weight rows per input row must fill whole slots");
   static_assert(A_BYTES % 1024 == 0 && (NT * 128) % 1024 == 0, "shifted A views must stay atom aligned");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
-  static_assert(!(PAIR == 2 && COUT == 64), "the 128->64 layer has its own 2-CTA kernel (convt_l4_ws.cu)");
+  static_assert(!(PAIR == 2 && COUT == 64), "the 128->64 layer has its own 2-CTA kernel (convt_l4_sw.cu)");
 };
 
 constexpr int kEpiWarps = 8;                 // warps 0..7, 2 per scheduler: warps e and e + 4 share a TMEM lane quarter

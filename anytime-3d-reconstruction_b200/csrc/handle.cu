@@ -96,13 +96,9 @@ struct a3d_handle {
   void* d_mt = nullptr; CUtensorMap tmap_a0, tmap_mt;                         // ... as a dense GEMM (tcgen05 path)
   ConvLayer conv[3];                                                           // stride-2 hidden layers
   float* d_w5 = nullptr;                                                       // final kernel [tap][ci] fp32
-  void* d_w5_16 = nullptr;                                                     // same, operand dtype (tcgen05 tail)
-  CUtensorMap tmap_a4, tmap_w5;                                                // tail: (c,w,h,d,n) view of act[4]; W5
-  void* d_w5_pair = nullptr;                                                   // pair tail (tail_tc2.cu): [Za 32 | Zm 16 | Zp 16] rows
-  CUtensorMap tmap_a4p, tmap_w5p;                                              // pair tail: (c,h,d,n,w) view of act[4]; its W5
-  CUtensorMap tmap_a4h;                                                        // same view, 64 x 32 x 4 x 1 x 4 boxes (HCOL mode)
-  bool tail_pair = false;                                                      // A3D_TAIL_IMPL=pair: 4 x 8 x 8 x 2-sample blocks
-  bool tail_v3 = false;                                                        // A3D_TAIL_IMPL=v3: always use tail_tc.cu
+  void* d_w5_hcol = nullptr;                                                   // tcgen05 tail (tail_hcol.cu): [Za0 16 | Za1 16 | Zm 16 | Zp 16] rows
+  CUtensorMap tmap_a4h, tmap_w5h;                                              // (c,h,d,n,w) view of act[4], 64 x 32 x 4 x 1 x 4 boxes; its W5
+  bool tail_simt = false;                                                      // A3D_TAIL_IMPL=simt: CUDA-core tail on the tcgen05 activations
   // arena
   int64_t max_chunk = 0;
   void* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // a0..a4
@@ -130,9 +126,8 @@ struct a3d_handle {
   int* d_progress = nullptr; // pacing counters of the w-sweep kernel (one int per cluster)
   int l4_pace = 8;           // sweep steps a cluster may run ahead of its peers (soft pacing, convt_l4_sw.cu);
                              // A3D_L4_PACE=<n> overrides, 0 switches pacing off
-  int l4_impl = 0;           // 128->64 layer: 0 = w-sweep 2-CTA kernel (convt_l4_sw.cu, default); A3D_L4_IMPL=ws: the
-                             // round-1 h-sweep kernel (convt_l4_ws.cu); A3D_L4_IMPL=generic: the 1-CTA kernel of the other
-                             // stride-2 layers (cross-checks; all three are parity-identical up to summation order)
+  int l4_impl = 0;           // 128->64 layer: 0 = w-sweep 2-CTA kernel (convt_l4_sw.cu, default); A3D_L4_IMPL=generic: the
+                             // 1-CTA kernel of the other stride-2 layers (cross-check; same values up to summation order)
 };
 
 namespace {
@@ -214,32 +209,6 @@ void pack_tc_weights(const std::vector<float>& wk, int cin, int cout, int fmt, s
             }
           }
       }
-  }
-}
-
-// Weight-stationary 2-CTA layout of the 128->64 layer (convt_l4_ws.cu): [class q = pd*2+ph][rank][sd][sh][chunk][128 rows]
-void pack_ws_weights(const std::vector<float>& wk, int cin, int cout, int fmt, std::vector<uint16_t>& out) {
-  const int chunks = cin / 64;
-  out.resize((size_t)4 * 2 * 4 * chunks * 128 * 64);
-  size_t row = 0;
-  for (int q = 0; q < 4; ++q) {
-    const int pd = q >> 1, ph = q & 1;
-    for (int rank = 0; rank < 2; ++rank)
-      for (int sd = 0; sd < 2; ++sd)
-        for (int sh = 0; sh < 2; ++sh) {
-          const int td = tap_of(pd, sd), th = tap_of(ph, sh);
-          for (int c = 0; c < chunks; ++c)
-            for (int r = 0; r < 128; ++r, ++row) {
-              int tw, co;
-              if (r < 64) { tw = rank == 0 ? 1 : 2; co = r; }            // dw = 0: rank 0 = pw0, rank 1 = pw1
-              else if (r < 96) { tw = 3; co = 32 * rank + (r - 64); }     // dw = -1 (pw0), N-half of this rank
-              else { tw = 0; co = 32 * rank + (r - 96); }                 // dw = +1 (pw1), N-half of this rank
-              const size_t tap = ((size_t)td * 4 + th) * 4 + tw;
-              const float* src = &wk[(tap * cout + co) * cin + (size_t)c * 64];
-              uint16_t* dst = &out[row * 64];
-              for (int i = 0; i < 64; ++i) dst[i] = cvt16(src[i], fmt);
-            }
-        }
   }
 }
 
@@ -378,20 +347,15 @@ int finalize_weights(a3d_handle* h) {
     if ((rc = upload(sf.data(), sf.size() * 4, (void**)&L.shift))) return rc;
     if ((rc = make_tmaps(h, li))) return rc;
     if (li == 2) {
-      pack_ws_weights(h->w[base], L.cin, L.cout, fmt, p16);
-      if ((rc = upload(p16.data(), p16.size() * 2, &L.wgt_ws))) return rc;
       EncodeTiledFn enc = get_encode_fn();
       const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-      cuuint64_t dims[2] = {64, (cuuint64_t)(p16.size() / 64)};
       cuuint64_t strides[1] = {128};
       cuuint32_t box[2] = {64, 256};
       cuuint32_t es[2] = {1, 1};
-      CUresult r = enc(&L.tmap_wgt_ws, dt, 2, L.wgt_ws, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(ws weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
       pack_sw_weights(h->w[base], L.cin, L.cout, fmt, p16);
       if ((rc = upload(p16.data(), p16.size() * 2, &L.wgt_sw))) return rc;
-      r = enc(&L.tmap_wgt_sw, dt, 2, L.wgt_sw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      cuuint64_t dims[2] = {64, (cuuint64_t)(p16.size() / 64)};
+      CUresult r = enc(&L.tmap_wgt_sw, dt, 2, L.wgt_sw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(sw weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
       const uint64_t W = L.win, C = L.cin;
@@ -407,38 +371,13 @@ int finalize_weights(a3d_handle* h) {
   // final kernel [4,4,4,1,64] is already [tap][ci]
   if ((rc = upload(h->w[26].data(), h->w[26].size() * 4, (void**)&h->d_w5))) return rc;
   {
-    // B operand of the tail GEMM: rows n = (td*4 + th)*2 + pw of  Wa (delta_w = 0, tap_w = pw + 1),
-    // Wb0 (delta_w = -1: tap_w 3 in the pw = 0 rows, zeros in pw = 1), Wb1 (delta_w = +1: tap_w 0 in the pw = 1 rows)
-    p16.assign((size_t)96 * 64, cvt16(0.f, fmt));
-    for (int td = 0; td < 4; ++td)
-      for (int th = 0; th < 4; ++th)
-        for (int pw = 0; pw < 2; ++pw) {
-          const int n = (td * 4 + th) * 2 + pw;
-          const float* wa = &h->w[26][(size_t)((td * 4 + th) * 4 + (pw + 1)) * 64];
-          const float* wb = &h->w[26][(size_t)((td * 4 + th) * 4 + (pw ? 0 : 3)) * 64];
-          for (int ci = 0; ci < 64; ++ci) {
-            p16[(size_t)n * 64 + ci] = cvt16(wa[ci], fmt);
-            p16[(size_t)((pw ? 64 : 32) + n) * 64 + ci] = cvt16(wb[ci], fmt);
-          }
-        }
-    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_16))) return rc;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return A3D_ERR_CUDA; }
     const CUtensorMapDataType dt = fmt == A3D_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    cuuint64_t dims[5] = {64, 32, 32, 32, (cuuint64_t)h->max_chunk};   // (c, h, d, w, n): GEMM rows come out w-slowest
-    cuuint64_t strides[4] = {128 * 32, 128 * 32 * 32, 128, 128ull * 32 * 32 * 32};
-    cuuint32_t box[5] = {64, 8, 8, 8, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&h->tmap_a4, dt, 5, h->act[4], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
-    cuuint64_t wd[2] = {64, 96};
     cuuint64_t ws[1] = {128};
-    cuuint32_t wb[2] = {64, 96};
-    r = enc(&h->tmap_w5, dt, 2, h->d_w5_16, wd, ws, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
-    // pair tail (tail_tc2.cu): B rows n = blk * 16 + td * 4 + j with th = (j + 1) & 3 (h taps in the order 1, 2, 3, 0):
+    CUresult r;
+    // B operand of the tail GEMM (tail_hcol.cu): rows n = blk * 16 + td * 4 + j with th = (j + 1) & 3 (h taps in the order 1, 2, 3, 0):
     // blk 0 = tap_w 1 (pw = 0, delta_w = 0), blk 1 = tap_w 2 (pw = 1, delta_w = 0), blk 2 = tap_w 3, blk 3 = tap_w 0
     p16.assign((size_t)64 * 64, cvt16(0.f, fmt));
     for (int td = 0; td < 4; ++td)
@@ -451,22 +390,18 @@ int finalize_weights(a3d_handle* h) {
           p16[(size_t)(48 + n) * 64 + ci] = cvt16(h->w[26][(size_t)(q * 4 + 0) * 64 + ci], fmt);
         }
       }
-    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_pair))) return rc;
-    cuuint64_t pd[5] = {64, 32, 32, (cuuint64_t)h->max_chunk, 32};   // (c, h, d, n, w): GEMM rows come out (w, sample, d, h)
+    if ((rc = upload(p16.data(), p16.size() * 2, &h->d_w5_hcol))) return rc;
+    cuuint64_t pd[5] = {64, 32, 32, (cuuint64_t)h->max_chunk, 32};   // (c, h, d, n, w): GEMM rows come out (w, d, h)
     cuuint64_t ps[4] = {128 * 32, 128 * 32 * 32, 128ull * 32 * 32 * 32, 128};
-    cuuint32_t pb[5] = {64, 8, 8, 2, 4};
-    r = enc(&h->tmap_a4p, dt, 5, h->act[4], pd, ps, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pair-tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
-    cuuint32_t hb[5] = {64, 32, 4, 1, 4};   // HCOL mode: rows (w, d, h) of one sample, the whole h axis per box
+    cuuint32_t hb[5] = {64, 32, 4, 1, 4};   // rows (w, d, h) of one sample, the whole h axis per box
     r = enc(&h->tmap_a4h, dt, 5, h->act[4], pd, ps, hb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(hcol-tail activations) failed: %d", (int)r); return A3D_ERR_CUDA; }
     cuuint64_t wpd[2] = {64, 64};
     cuuint32_t wpb[2] = {64, 64};
-    r = enc(&h->tmap_w5p, dt, 2, h->d_w5_pair, wpd, ws, wpb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    r = enc(&h->tmap_w5h, dt, 2, h->d_w5_hcol, wpd, ws, wpb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(pair-tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(tail weights) failed: %d", (int)r); return A3D_ERR_CUDA; }
   }
   h->dirty = false;
   return A3D_OK;
@@ -498,9 +433,6 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
     else if (li == 2 && h->l4_impl == 0)
       rc = launch_convt_l4_sw(h->conv[li].tmap_act_sw, h->conv[li].tmap_wgt_sw, h->act[li + 2], h->conv[li].scale,
                               h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, h->d_progress, h->l4_pace, st, &h->launches);
-    else if (li == 2 && h->l4_impl == 1)
-      rc = launch_convt_l4_ws(h->conv[li].tmap_act, h->conv[li].tmap_wgt_ws, h->act[li + 2], h->conv[li].scale,
-                              h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
     else
       rc = launch_convt_s2_tc(h->conv[li], h->act[li + 2], n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
     if (rc) return rc;
@@ -513,19 +445,13 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
 int run_tail(a3d_handle* h, int64_t B, int K, const uint8_t* bits, float thr, unsigned long long* counts, float* mean,
              float gamma, double* loss, cudaStream_t st) {
   const int sig = h->desc.final_activation == A3D_FINAL_SIGMOID;
-  if (h->desc.impl == A3D_IMPL_SIMT)
+  // A3D_TAIL_IMPL=simt: the CUDA-core tail on the activations of the tcgen05 layers (on-device cross-check of the
+  // tensor-core tail in isolation, tests/test_gpu_parity.py)
+  if (h->desc.impl == A3D_IMPL_SIMT || h->tail_simt)
     return launch_tail(h->act[4], h->d_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss, st,
                        &h->launches);
-  // default: one-sample blocks with the whole h axis per tile (any K).  A3D_TAIL_IMPL=pair: the two-sample / two-object
-  // blocks (even K, K = 1); A3D_TAIL_IMPL=v3 or odd K >= 3 under "pair": the three-view kernel of tail_tc.cu
-  if (!h->tail_v3 && !h->tail_pair)
-    return launch_tail_pair(h->tmap_a4h, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
-                            loss, h->num_sms, true, st, &h->launches);
-  if ((K == 1 || (K & 1) == 0) && !h->tail_v3 && h->max_chunk >= 2)
-    return launch_tail_pair(h->tmap_a4p, h->tmap_w5p, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
-                            loss, h->num_sms, false, st, &h->launches);
-  return launch_tail_tc(h->tmap_a4, h->tmap_w5, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma, loss,
-                        h->num_sms, st, &h->launches);
+  return launch_tail_hcol(h->tmap_a4h, h->tmap_w5h, B, K, h->desc.operand_dtype, sig, bits, thr, counts, mean, gamma,
+                          loss, h->num_sms, st, &h->launches);
 }
 
 void collect_profile(a3d_handle* h, cudaStream_t st, bool first) {
@@ -615,14 +541,14 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   h->dense_units = h->grid0 * h->grid0 * h->grid0 * h->ch0;  // :120
   build_weight_table(h);
   h->max_chunk = d->max_chunk;
-  { const char* e = getenv("A3D_L4_IMPL"); h->l4_impl = !e ? 0 : std::string(e) == "generic" ? 2 : std::string(e) == "ws" ? 1 : 0; }
+  { const char* e = getenv("A3D_L4_IMPL"); h->l4_impl = (e && std::string(e) == "generic") ? 2 : 0; }
   { const char* e = getenv("A3D_L4_PACE"); if (e) h->l4_pace = atoi(e); }
   if (cudaMalloc(&h->d_progress, convt_l4_sw_progress_bytes()) != cudaSuccess) {
     set_error("allocation of the pacing counters failed");
     a3d_destroy(h);
     return A3D_ERR_CUDA;
   }
-  { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_v3 = e && std::string(e) == "v3"; h->tail_pair = e && std::string(e) == "pair"; }
+  { const char* e = getenv("A3D_TAIL_IMPL"); h->tail_simt = e && std::string(e) == "simt"; }
   const int geo[3][3] = {{512, 256, 4}, {256, 128, 8}, {128, 64, 16}};
   for (int i = 0; i < 3; ++i) { h->conv[i].cin = geo[i][0]; h->conv[i].cout = geo[i][1]; h->conv[i].win = geo[i][2]; }
   h->act_elems[0] = 512; h->act_elems[1] = 64 * 512; h->act_elems[2] = 512 * 256; h->act_elems[3] = 4096 * 128;
@@ -649,8 +575,8 @@ void a3d_destroy(a3d_handle* h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 5; ++i) cudaFree(h->act[i]);
   cudaFree(h->d_wd); cudaFree(h->d_bd); cudaFree(h->d_s0); cudaFree(h->d_h0);
-  cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_16); cudaFree(h->d_w5_pair);
-  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_ws); cudaFree(L.wgt_sw); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
+  cudaFree(h->d_mt); cudaFree(h->d_w1_tco); cudaFree(h->d_s1); cudaFree(h->d_h1); cudaFree(h->d_w5); cudaFree(h->d_w5_hcol);
+  for (auto& L : h->conv) { cudaFree(L.wgt_packed); cudaFree(L.wgt_sw); cudaFree(L.wgt_tco); cudaFree(L.scale); cudaFree(L.shift); }
   cudaFree(h->st_z); cudaFree(h->st_mask); cudaFree(h->st_mu); cudaFree(h->st_zout); cudaFree(h->st_mean);
   cudaFree(h->st_bits); cudaFree(h->st_counts);
   cudaFree(h->d_progress);

@@ -74,8 +74,6 @@ struct ConvLayer {
   CUtensorMap tmap_wgt;   // 2-D view (64 ci, rows) of the per-(parity,tap,chunk) repacked weights, box (64, 256), SW128
   CUtensorMap tmap_wgt64; // same tensor, box (64, 64): N-half loads of the 2-CTA path
   void* wgt_packed = nullptr;   // device, 16-bit
-  CUtensorMap tmap_wgt_ws;      // weight-stationary 2-CTA layout (128->64 layer only, convt_l4_ws.cu)
-  void* wgt_ws = nullptr;
   CUtensorMap tmap_act_sw;      // w-sweep kernel (convt_l4_sw.cu): (c, n, h, w, d) view, box (64, 8, W+2, 1, 1)
   CUtensorMap tmap_wgt_sw;      // ... its resident weights: [class][rank][sd][sh][chunk][2 taps x 64 co] rows
   void* wgt_sw = nullptr;
@@ -94,9 +92,6 @@ int launch_gemm_l1(const CUtensorMap& tmap_a0, const CUtensorMap& tmap_mt, void*
                    int64_t* launches);
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches);
-int launch_convt_l4_ws(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
-                       const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
-                       cudaStream_t st, int64_t* launches);
 int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
                        const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, int* progress,
                        int pace_delta, cudaStream_t st, int64_t* launches);
@@ -107,14 +102,10 @@ int launch_convt_s2_simt(const ConvLayer& L, const void* in, void* out, int64_t 
 int launch_tail(const void* a4, const float* w5, int64_t B, int K, int fmt, int final_sigmoid,
                 const uint8_t* target_bits, float thr, unsigned long long* counts, float* mean_prob, float gamma,
                 double* loss, cudaStream_t st, int64_t* launches);
-int launch_tail_tc(const CUtensorMap& tmap_a4, const CUtensorMap& tmap_w5, int64_t B, int K, int fmt,
-                   int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                   float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches);
-// pair variant (tail_tc2.cu, even K): tmap_a4p = (c,h,d,n,w) view with box (64,8,8,2,4); tmap_w5p = 64-row weight tile
-int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, int64_t B, int K, int fmt,
+// tcgen05 tail (tail_hcol.cu): tmap_a4h = (c,h,d,n,w) view of act[4] with box (64,32,4,1,4); tmap_w5h = 64-row weight tile
+int launch_tail_hcol(const CUtensorMap& tmap_a4h, const CUtensorMap& tmap_w5h, int64_t B, int K, int fmt,
                      int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                     float* mean_prob, float gamma, double* loss, int num_sms, bool hcol, cudaStream_t st,
-                     int64_t* launches);
+                     float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches);
 int launch_binary_loss(const float* pred, const float* target, int64_t B, int64_t V, float gamma, double* loss,
                        cudaStream_t st, int64_t* launches);
 int launch_counts_sweep(const float* target, const float* pred, int64_t B, int64_t V, const float* thr, int T, int strict,

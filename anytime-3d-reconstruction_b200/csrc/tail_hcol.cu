@@ -1,13 +1,12 @@
-// Fused tail (default kernel, three block shapes) -- same maths as tail_tc.cu:
+// Fused tail (the tcgen05 tail kernel):
 //   final Conv3DTranspose(64 -> 1, k4, s2, 'same', no bias, no BN) + tf.sigmoid   autoencoder3D.py:129-136
 //   mean over the K post-sigmoid grids of an object                                 nolbo_test.py:167-177
 //   yPred = (mean >= thr), TP / FP / FN (+ weighted BCE) against the bit-packed target   function.py:100-115,73-82
-// with every activation tile read ONCE by the tensor core (tail_tc.cu reads it three times through w-shifted descriptor
-// views with N = 32 MMAs).
+// with every activation tile read ONCE by the tensor core.
 //
-// A CTA block is four w-slices of 128 GEMM rows; M-tile m is exactly w-slice m.  The rows of a tile are
-//   MODE_HCOL (default, any K):  (d 4, h 32) of ONE sample -- a warp is one d line with the whole h axis, no h halo;
-//   MODE_PAIR / MODE_PAIR1:      (sample 2, d 8, h 8) -- two samples of one object (even K) or two consecutive objects (K = 1).
+// A CTA block is 4 (w) x 4 (d) x 32 (h) input voxels of ONE sample = four w-slices of 128 GEMM rows; M-tile m is exactly
+// w-slice m and the rows of a tile are (d 4, h 32): a warp (32 TMEM lanes) is one d line with the WHOLE h axis, so there
+// is no h halo and any K works.
 // ONE MMA per (tile, K step) with N = 64:
 //   columns  0..15  Za0[(td, j)]  = X . W[td, th(j), tap_w = 1]        (delta_w = 0, output parity pw = 0)
 //   columns 16..31  Za1[(td, j)]  = X . W[td, th(j), tap_w = 2]        (delta_w = 0, output parity pw = 1)
@@ -18,10 +17,12 @@
 // register PAIR and is issued as one packed add.rn.f32x2 (FADD2).
 // The w-axis col2im is then free: the accumulators of slices m - 1, m, m + 1 live in the SAME TMEM lanes, in different
 // column blocks, so the epilogue thread of (slice m, row r) simply loads Za from block m, Zm from block m - 1 and Zp
-// from block m + 1.  h axis by warp shuffles, d axis by one shared-memory exchange.  Blocks advance by 3 slices in w
-// (6 complete output columns) and by 3 (HCOL) or 7 (PAIR) voxels in d / 7 in h (PAIR).
-// What bounds the kernel is the activation bytes that cross the L2 -> SM fabric (halo rows) and the shared-memory port
-// (TMA writes + operand reads + exchange); see profiles/r01_notes.md for the ablations.
+// from block m + 1.  h axis by warp shuffles (lanes 0 / 31 sit on the grid border: their missing neighbour is the zero
+// padding), d axis by one shared-memory exchange between the four warps of a tile (128-thread named barrier).  Blocks
+// advance by 3 slices in w (6 complete output columns) and by 3 voxels in d.
+// What bounds the kernel is the HBM -> L2 -> SM path (17.2 GB of activations per 4096 decodes, read once from DRAM);
+// see profiles/r01_notes.md and r02_notes.md for the ablations (pair blocks, three-view kernel, w-sweep: all measured,
+// none kept -- this is the only tcgen05 tail in the library; csrc/tail.cu is the CUDA-core cross-check).
 #include <cstdlib>
 #include <type_traits>
 
@@ -32,17 +33,10 @@
 namespace a3d {
 namespace {
 
-constexpr int kBw = 4, kBd = 8, kBh = 8;
-constexpr int kRows = kBw * 2 * kBd * kBh;       // 512 GEMM rows = 4 M-tiles of 128
-constexpr int kBlocksW = 11, kBlocksDH = 5;      // w origins -1 + 3i (i < 11), d / h origins -1 + 7i (i < 5)
-constexpr int kItemsPair = kBlocksW * kBlocksDH * kBlocksDH;   // 275 blocks of 4 x 8 x 8 x 2 samples
-constexpr int kBlocksD4 = 11;                                   // HCOL: d origins -1 + 3i (i < 11), h complete
-constexpr int kItemsHcol = kBlocksW * kBlocksD4;                // 121 blocks of 4 (w) x 4 (d) x 32 (h) x 1 sample
-// MODE_PAIR: two samples of one object per block (even K);  MODE_PAIR1: K = 1, two consecutive objects per block;
-// MODE_HCOL: one sample per block, tile rows = (d 4, h 32): the whole h axis sits in the 32 lanes of a warp, so there is
-// no h halo (61,952 instead of 70,400 rows per decode cross the L2->SM fabric, which is what bounds this kernel) and any
-// K works; the d exchange couples the four warps of a tile (128-thread named barrier).
-enum { MODE_PAIR = 0, MODE_PAIR1 = 1, MODE_HCOL = 2 };
+constexpr int kRows = 512;                       // 4 (w) x 4 (d) x 32 (h) GEMM rows = 4 M-tiles of 128
+constexpr int kBlocksW = 11;                     // w origins -1 + 3i (i < 11)
+constexpr int kBlocksD4 = 11;                    // d origins -1 + 3i (i < 11), h complete
+constexpr int kItemsPerObj = kBlocksW * kBlocksD4;   // 121 blocks per sample
 constexpr int kABytes = kRows * 128;             // 64 KB per stage
 constexpr int kWRows = 64;
 constexpr int kWBytes = kWRows * 128;
@@ -51,20 +45,14 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 640
 constexpr int kSmem = 1024 + 2 * kABytes + kWBytes + 2 * kExD + 16 * 8 + 16;
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory"); }
-// The d-axis exchange only couples rows r and r +- 8 of one 64-row (d, h) plane group = the two epilogue warps 2j, 2j + 1:
-// a 64-thread named barrier per warp pair (ids 2..9) instead of a 512-thread barrier per sample
-__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory"); }
 __device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory"); }
 
 // SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 / 3 = sigmoid
 // as 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities (2) or the BCE loss (3) are
 // emitted; the loss code is compiled out of 2)
-// MODE_PAIR1: K == 1 -- the two row slots hold two CONSECUTIVE OBJECTS (2j, 2j + 1) instead of two samples of one object;
-// no slot combine and no block-wide barrier, every slot finalizes its own object.
-template <int FMT, int SIG, int MODE>
+template <int FMT, int SIG>
 __global__ void __launch_bounds__(kThreads, 1)
-tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
+tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_constant__ CUtensorMap tmap_w5, int64_t B,
                  int K, const uint8_t* __restrict__ target_bits, float thr,
                  unsigned long long* __restrict__ counts, float* __restrict__ mean_prob, float gamma,
                  double* __restrict__ loss) {
@@ -83,10 +71,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr bool K1 = MODE == MODE_PAIR1, HCOL = MODE == MODE_HCOL;
-  constexpr int kItemsPerObj = HCOL ? kItemsHcol : kItemsPair;
-  const int64_t total_items = (K1 ? (B + 1) / 2 : B) * kItemsPerObj;
-  const int pairs = K1 ? 1 : HCOL ? K : K >> 1;   // block iterations per item
+  const int64_t total_items = B * kItemsPerObj;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a4);
@@ -123,15 +108,14 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int b = (int)item / kItemsPerObj;    // the launcher guarantees total_items < 2^31: 32-bit division by a constant
       const int blk = (int)item - b * kItemsPerObj;
-      const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
-      const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
-      for (int kp = 0; kp < pairs; ++kp, ++it) {
+      const int aw = -1 + 3 * (blk % kBlocksW), ad = -1 + 3 * (blk / kBlocksW);
+      for (int kp = 0; kp < K; ++kp, ++it) {
         const int s = it & 1;
         ptx::mbar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&a_full[s], kABytes);
-          // tensor-map dims are (c, h, d, n, w): rows land as (w, sample, d, h) with h fastest (HCOL: box 64 x 32 x 4 x 1 x 4)
-          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, ah, ad, K1 ? 2 * b : HCOL ? b * K + kp : b * K + 2 * kp, aw);
+          // tensor-map dims are (c, h, d, n, w), box 64 x 32 x 4 x 1 x 4: rows land as (w, d, h) with h fastest
+          ptx::tma_load_5d(smem_a + s * kABytes, &tmap_a4, &a_full[s], 0, 0, ad, b * K + kp, aw);
         }
         __syncwarp();
       }
@@ -144,7 +128,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
-      for (int kp = 0; kp < pairs; ++kp, ++it) {
+      for (int kp = 0; kp < K; ++kp, ++it) {
         const int s = it & 1;
         ptx::mbar_wait(&t_empty[s], ((it >> 1) & 1) ^ 1);
         ptx::mbar_wait(&a_full[s], (it >> 1) & 1);
@@ -170,34 +154,33 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     const int e = warp - 4;
     const int m = e >> 2;                      // M-tile = w-slice of the block
     const int quarter = e & 3;                 // TMEM lane quarter == warp % 4
-    const int rt = quarter * 32 + lane;        // row in the tile: sample * 64 + ld * 8 + lh
+    const int rt = quarter * 32 + lane;        // row in the tile: ld * 32 + lh
     const int r = m * 128 + rt;                // row in the block
-    const int slot = HCOL ? 0 : rt >> 6, ld = HCOL ? quarter : (rt >> 3) & 7, lh = HCOL ? lane : rt & 7, lw = m;
-    constexpr int kDStep = HCOL ? 32 : 8, kDLast = HCOL ? 3 : 7;   // rows between d neighbours; last d index of a tile
+    const int ld = quarter, lh = lane, lw = m;
+    constexpr int kDStep = 32, kDLast = 3;     // rows between d neighbours; last d index of a tile
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float invk = 1.f / (float)K;
     // d - 1 / d + 1 neighbours (same sample).  Rows at the d border of the block read their own slot instead: those sums
     // only reach outputs that the `ok` mask below drops
     const int rm = ld >= 1 ? r - kDStep : r, rp = ld < kDLast ? r + kDStep : r;
-    // HCOL: lanes 0 / 31 sit on the grid border in h, their missing neighbour is the zero padding
-    const uint64_t hmask = ptx::f2_pack(!HCOL || lane >= 1 ? 1.f : 0.f, !HCOL || lane <= 30 ? 1.f : 0.f);
+    // lanes 0 / 31 sit on the grid border in h, their missing neighbour is the zero padding
+    const uint64_t hmask = ptx::f2_pack(lane >= 1 ? 1.f : 0.f, lane <= 30 ? 1.f : 0.f);
     const uint64_t half2 = ptx::f2_pack(0.5f, 0.5f);
     uint64_t* exq = reinterpret_cast<uint64_t*>(exD);   // exchange buffers as (ph = 0, ph = 1) pairs: [2][4][kRows]
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int b = (int)item / kItemsPerObj;    // the launcher guarantees total_items < 2^31: 32-bit division by a constant
       const int blk = (int)item - b * kItemsPerObj;
-      const int aw = -1 + 3 * (blk % kBlocksW), ah = HCOL ? 0 : -1 + 7 * ((blk / kBlocksW) % kBlocksDH);
-      const int ad = HCOL ? -1 + 3 * (blk / kBlocksW) : -1 + 7 * (blk / (kBlocksW * kBlocksDH));
+      const int aw = -1 + 3 * (blk % kBlocksW), ad = -1 + 3 * (blk / kBlocksW);
       // this row's 2 x 2 x 2 outputs: od = 2 * d0 + pd, ...; an output is complete when the neighbour row on that side is
       // inside the block (or the output itself lies outside the grid and is dropped).  The target bytes (one per (pd, ph):
       // the pw = 0 / 1 outputs are adjacent bits) are fetched NOW so that their latency hides behind the K samples
-      const int64_t obj = K1 ? 2 * (int64_t)b + slot : b;
-      const bool fin = K1 ? obj < B : HCOL ? true : slot == 0;
-      const int d0 = ad + ld, h0 = ah + lh, w0 = aw + lw;
-      const bool ind = (unsigned)d0 < 32u, inh = (unsigned)h0 < 32u, inw = (unsigned)w0 < 32u;
+      const int64_t obj = b;
+      constexpr bool fin = true;
+      const int d0 = ad + ld, h0 = lh, w0 = aw + lw;
+      const bool ind = (unsigned)d0 < 32u, inw = (unsigned)w0 < 32u;
       const bool okd[2] = {ind && ld >= 1, ind && ld < kDLast};
-      const bool okh[2] = {inh && (HCOL || lh >= 1), inh && (HCOL || lh <= 6)};
+      const bool okh[2] = {true, true};
       const bool okw[2] = {inw && lw >= 1, inw && lw <= 2};
       const int vbase = (2 * d0 * 64 + 2 * h0) * 64 + 2 * w0;
       const int bit0 = (2 * w0) & 7;
@@ -212,7 +195,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       uint64_t psum[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) psum[p] = 0ull;
-      for (int kp = 0; kp < pairs; ++kp, ++it) {
+      for (int kp = 0; kp < K; ++kp, ++it) {
         const int s = it & 1;
         ptx::mbar_wait(&t_full[s], (it >> 1) & 1);
         ptx::tc_fence_after();
@@ -228,7 +211,7 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   // accumulators are in registers: release the TMEM buffer
-        // ---- w axis (register pairs) and h axis (lanes are 8 consecutive h):
+        // ---- w axis (register pairs) and h axis (lanes are the 32 h positions):
         //      out_h[ph=0] = Z[th=1] + Z_{h-1}[th=3];  out_h[ph=1] = Z[th=2] + Z_{h+1}[th=0]
         uint64_t zh[4][2];   // [td][pw] as (ph = 0, ph = 1)
 #pragma unroll
@@ -243,18 +226,16 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             ptx::f2_unpack(o, o3, o0);
             const float up = __shfl_up_sync(0xffffffffu, o3, 1);
             const float dn = __shfl_down_sync(0xffffffffu, o0, 1);
-            if constexpr (HCOL) zh[td][pw] = ptx::f2_fma(ptx::f2_pack(up, dn), hmask, c);
-            else zh[td][pw] = ptx::f2_add(c, ptx::f2_pack(up, dn));
+            zh[td][pw] = ptx::f2_fma(ptx::f2_pack(up, dn), hmask, c);
           }
-        // ---- d axis through shared memory (double buffered across pairs: one warp-pair sync per pair)
+        // ---- d axis through shared memory (double buffered across samples: one tile barrier per sample)
         uint64_t* ex = exq + (it & 1) * (4 * kRows);
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw) {
           ex[(0 * 2 + pw) * kRows + r] = zh[3][pw];
           ex[(1 * 2 + pw) * kRows + r] = zh[0][pw];
         }
-        if constexpr (HCOL) tile_sync(m);
-        else pair_sync(e >> 1);
+        tile_sync(m);
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw) {
           uint64_t o0 = ptx::f2_add(zh[1][pw], ex[(0 * 2 + pw) * kRows + rm]);
@@ -274,20 +255,6 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           }
           psum[0 * 2 + pw] = ptx::f2_add(psum[0 * 2 + pw], o0);
           psum[1 * 2 + pw] = ptx::f2_add(psum[1 * 2 + pw], o1);
-        }
-      }
-      // ---- K >= 2: combine the two sample slots (rows r and r + 64 of a tile) through shared memory and finalize in
-      //      slot 0;  K == 1: each slot finalizes its own object.  `slot` is uniform per warp.
-      if constexpr (MODE == MODE_PAIR) {
-        uint64_t* ex = exq + (it & 1) * (4 * kRows);   // the buffer the NEXT pair would use: its last readers finished two syncs ago
-        if (slot == 1) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) ex[p * kRows + r] = psum[p];
-        }
-        epi_sync();
-        if (fin) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) psum[p] = ptx::f2_add(psum[p], ex[p * kRows + r + 64]);
         }
       }
       if constexpr (SIG == 1) {
@@ -405,7 +372,6 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           }
         }
       }
-      if constexpr (MODE == MODE_PAIR) epi_sync();   // the slot exchange buffer is reused by the next item's d-exchange
     }
   }
 
@@ -416,38 +382,29 @@ tail_pair_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
 
 }  // namespace
 
-int launch_tail_pair(const CUtensorMap& tmap_a4p, const CUtensorMap& tmap_w5p, int64_t B, int K, int fmt,
+int launch_tail_hcol(const CUtensorMap& tmap_a4h, const CUtensorMap& tmap_w5p, int64_t B, int K, int fmt,
                      int final_sigmoid, const uint8_t* target_bits, float thr, unsigned long long* counts,
-                     float* mean_prob, float gamma, double* loss, int num_sms, bool hcol, cudaStream_t st,
-                     int64_t* launches) {
+                     float* mean_prob, float gamma, double* loss, int num_sms, cudaStream_t st, int64_t* launches) {
   if (B <= 0) return A3D_OK;
-  if (!hcol && K != 1 && (K & 1)) { set_error("tail_pair: K must be 1 or even"); return A3D_ERR_INVALID; }
-  const int mode = hcol ? MODE_HCOL : K == 1 ? MODE_PAIR1 : MODE_PAIR;
-  const int64_t items = mode == MODE_HCOL ? B * kItemsHcol : (mode == MODE_PAIR1 ? (B + 1) / 2 : B) * kItemsPair;
+  const int64_t items = B * kItemsPerObj;
   if (items > 0x7fffffffll || B * (int64_t)K > 0x7fffffffll) { set_error("tail: batch too large for one launch"); return A3D_ERR_INVALID; }
   const int grid = (int)(items < num_sms ? items : num_sms);
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), kSmem, st, 1, tmap_a4p, tmap_w5p, B, K, target_bits, thr,
+    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), kSmem, st, 1, tmap_a4h, tmap_w5p, B, K, target_bits, thr,
                              counts, mean_prob, gamma, loss));
     return A3D_OK;
   };
   // sigmoid mode: 1 = tanh form for the counts-only path, 2 = exp form whenever probabilities or the loss are emitted
   const int sig = !final_sigmoid ? 0 : loss ? 3 : mean_prob ? 2 : 1;
-  auto pick = [&](auto fmt_c, auto mode_c) -> int {
+  auto pick = [&](auto fmt_c) -> int {
     constexpr int F = decltype(fmt_c)::value;
-    constexpr int M = decltype(mode_c)::value;
-    return sig == 0 ? launch(tail_pair_kernel<F, 0, M>)
-                    : sig == 1 ? launch(tail_pair_kernel<F, 1, M>)
-                               : sig == 2 ? launch(tail_pair_kernel<F, 2, M>) : launch(tail_pair_kernel<F, 3, M>);
+    return sig == 0 ? launch(tail_hcol_kernel<F, 0>)
+                    : sig == 1 ? launch(tail_hcol_kernel<F, 1>)
+                               : sig == 2 ? launch(tail_hcol_kernel<F, 2>) : launch(tail_hcol_kernel<F, 3>);
   };
-  auto pick_mode = [&](auto fmt_c) -> int {
-    return mode == MODE_HCOL ? pick(fmt_c, std::integral_constant<int, MODE_HCOL>{})
-                             : mode == MODE_PAIR1 ? pick(fmt_c, std::integral_constant<int, MODE_PAIR1>{})
-                                                  : pick(fmt_c, std::integral_constant<int, MODE_PAIR>{});
-  };
-  const int rc = fmt == A3D_DTYPE_F16 ? pick_mode(std::integral_constant<int, A3D_DTYPE_F16>{})
-                                      : pick_mode(std::integral_constant<int, A3D_DTYPE_BF16>{});
+  const int rc = fmt == A3D_DTYPE_F16 ? pick(std::integral_constant<int, A3D_DTYPE_F16>{})
+                                      : pick(std::integral_constant<int, A3D_DTYPE_BF16>{});
   if (rc == A3D_OK && launches) ++*launches;
   return rc;
 }

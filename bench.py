@@ -628,7 +628,7 @@ def _main(args, saved_stdout):
                 'traffic_source': t_l4.get('source'), 'algorithmic_bytes_per_launch': decodes_per_launch * 5_242_880,
                 'peak_source': f'{src} sustained bf16', 'stage_ms': stage,
                 'decoder_tflops_all_stages': FLOP_PER_DECODE * decodes_per_launch / (sum(stage.values()) * 1e-3) / 1e12,
-                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_pair_kernel<MODE_HCOL> (final ConvT + sigmoid + K-mean + threshold + counts)',
+                'fused_tail': {'bound': 'hbm', 'kernel': 'tail_hcol_kernel (final ConvT + sigmoid + K-mean + threshold + counts)',
                                'achieved': tail_gbs, 'peak': hpeak, 'unit': 'GB/s', 'frac': tail_gbs / hpeak,
                                'traffic': t_tail.get('dram_bytes'), 'traffic_source': t_tail.get('source'),
                                'algorithmic_bytes_per_launch': tail_bytes}}

@@ -1,6 +1,6 @@
 """Cross-check of the 128->64 layer kernels on the device (diagnostic).  The layer implementation is chosen at handle
-creation by A3D_L4_IMPL (unset = w-sweep kernel convt_l4_sw.cu, 'ws' = round-1 h-sweep kernel, 'generic' = 1-CTA
-kernel); this script decodes the same latents with each, compares the 32^3 x 64 activations with each other and with
+creation by A3D_L4_IMPL (unset = w-sweep kernel convt_l4_sw.cu, 'generic' = 1-CTA kernel of
+convt_tc.cu); this script decodes the same latents with each, compares the 32^3 x 64 activations with each other and with
 the oracle, localises mismatches (by decode, parity class, d, h, w, channel) and times the layer on a full chunk.
 
 Usage: python tests/tools/l4_check.py [n_small] [n_big] [reps]"""
@@ -52,20 +52,20 @@ _, layers = dr.decoder_forward(st, ws, z, return_layers=True)
 ref = layers[4].numpy()
 outs = {}
 ok = True
-for impl in (None, 'ws'):
+for impl in (None, 'generic'):
     d = make(impl, 32)
     d(torch.from_numpy(z).cuda())     # one chunk through a3d_decode (the numpy path decodes in sub-chunks)
     torch.cuda.synchronize()
     outs[impl] = d.debug_layer(4, n)
     ok &= localise(f'L4 impl={impl or "sw"} vs oracle (n={n})', outs[impl], ref)
     del d
-ok &= localise('L4 sw vs ws', outs[None], outs['ws'])
-print('exact equal fraction sw vs ws', float((outs[None] == outs['ws']).mean()))
+ok &= localise('L4 sw vs generic', outs[None], outs['generic'])
+print('exact equal fraction sw vs generic', float((outs[None] == outs['generic']).mean()))
 
 if n_big > 0:
     zc = torch.from_numpy(rng.standard_normal((n_big, 1, 64)).astype(np.float32)).cuda()
     bits = torch.zeros((n_big, 32768), dtype=torch.uint8, device='cuda')
-    for impl in (None, 'ws'):
+    for impl in (None, 'generic'):
         d = make(impl, n_big)
         d.set_profiling(True)
         rec = []
