@@ -5,7 +5,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liba3d.so')
+# A3D_LIB selects another build of the same library in the package directory (liba3d_checked.so: the bounds-checked
+# build of tests/test_gpu_checked_build.py); there is still no non-CUDA implementation behind this binding.
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get('A3D_LIB', 'liba3d.so')))
 A3D_ABI_VERSION = 1
 A3D_MAX_LAYERS = 8
 VOXELS = 262144

@@ -75,6 +75,7 @@ impute_kernel(const float* __restrict__ z, const float* __restrict__ mask, const
       } else if (fill == A3D_FILL_NORMAL) {
         if (v == 0.f) v = nrm[e];                                      // nolbo.py:437-439
       }
+      A3D_DEV_CHECK(k >= 0 && k < K && d >= 0 && d < D && (fill != A3D_FILL_PRIOR_SAMPLE || (unsigned)cstar_s < (unsigned)C));
       z_out[((size_t)b * K + k) * D + d] = v;
     }
   }

@@ -441,6 +441,8 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             const int grow = quarter * 32 + r;          // GEMM row = (h, decode)
             const int h = grow / NT, nr = nb * NT + grow % NT;
             if (nr < n_alloc) {
+              A3D_DEV_CHECK(nr >= 0 && (unsigned)(2 * d + pd) < (unsigned)OD && (unsigned)(2 * h + ph) < (unsigned)OD &&
+                            (unsigned)ow < (unsigned)OD && co + c16 * 8 + 8 <= COUT);
               const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + ow;
               __stcs(reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8), val);
             }

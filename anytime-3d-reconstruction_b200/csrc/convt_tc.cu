@@ -334,6 +334,8 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           const int grow = quarter * 32 + r;
           const int wr = grow / NT, nr = nb * NT + grow % NT;
           if (nr < n_alloc) {
+            A3D_DEV_CHECK(nr >= 0 && (unsigned)(2 * d + pd) < (unsigned)OD && (unsigned)(2 * h + ph) < (unsigned)OD &&
+                          (unsigned)(2 * wr + pw) < (unsigned)OD && co >= 0 && co + c16 * 8 + 8 <= COUT);
             const size_t vox = (((size_t)nr * OD + (2 * d + pd)) * OD + (2 * h + ph)) * OD + (2 * wr + pw);
             __stcs(reinterpret_cast<uint4*>(out + vox * COUT + co + c16 * 8), val);   // streaming: keep L2 for the inputs
           }

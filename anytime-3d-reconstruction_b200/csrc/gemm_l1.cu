@@ -164,6 +164,7 @@ gemm_l1_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
           const int c16 = lane & 7;
           const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c16 ^ (r & 7)) * 16));
           const int n = mt * BM + quarter * 32 + r;
+          A3D_DEV_CHECK(col0 >= 0 && col0 + c16 * 8 + 8 <= NDIM && n >= 0);
           if (n < n_rows) *reinterpret_cast<uint4*>(out + (size_t)n * NDIM + col0 + c16 * 8) = val;
         }
         __syncwarp();

@@ -500,9 +500,22 @@ uint32_t a3d_crc32c(const void* data, size_t n, uint32_t crc) {
 }
 const char* a3d_last_error(void) { return g_err; }
 
+#ifdef A3D_CHECKED
+namespace { __global__ void checked_selftest_kernel(int v) { A3D_DEV_CHECK(v < 0); } }
+#endif
+
 int a3d_create(const a3d_desc* d, a3d_handle** out) {
   if (!d || !out) { set_error("null argument"); return A3D_ERR_INVALID; }
   *out = nullptr;
+#ifdef A3D_CHECKED
+  // proof that the range checks of this build are live: A3D_CHECK_SELFTEST=1 runs a kernel whose check must fail
+  if (getenv("A3D_CHECK_SELFTEST") && atoi(getenv("A3D_CHECK_SELFTEST")) == 1) {
+    checked_selftest_kernel<<<1, 1>>>(1);
+    A3D_CUDA_OK(cudaDeviceSynchronize());
+    set_error("checked build: the self-test check did not trap");
+    return A3D_ERR_INVALID;
+  }
+#endif
   if (d->abi_version != A3D_ABI_VERSION) { set_error("ABI version mismatch: %d vs %d", d->abi_version, A3D_ABI_VERSION); return A3D_ERR_INVALID; }
   // supported structure: the decoder every reference script builds (autoencoder3D.py:15-24; test_*_VAE*.py configs)
   static const int kF[5] = {512, 256, 128, 64, 1}, kS[5] = {1, 2, 2, 2, 2};

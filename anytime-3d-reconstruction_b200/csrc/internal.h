@@ -24,6 +24,26 @@ void set_error(const char* fmt, ...);
 
 constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default epsilon
 
+// Checked build (`python anytime-3d-reconstruction_b200/build.py --checked` -> liba3d_checked.so, -DA3D_CHECKED): every
+// hand-computed global-memory index of the decoder kernels (epilogue stores, target-bit reads, probability stores, count
+// atomics, imputation outputs) and every shared-memory staging offset is range-checked on the device and traps with a
+// message.  compute-sanitizer is closed on the GPU pool this was developed on; tests/test_gpu_checked_build.py runs the
+// ragged / border cases of the parity suite through this build instead.  TMA loads need no check: the tensor map bounds
+// them in hardware (out-of-range elements are zero filled = the 'same' padding).  The release build compiles the
+// checks out.
+#ifdef A3D_CHECKED
+#define A3D_DEV_CHECK(cond)                                                                                        \
+  do {                                                                                                             \
+    if (!(cond)) {                                                                                                 \
+      printf("A3D_DEV_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x,   \
+             (int)threadIdx.x);                                                                                    \
+      __trap();                                                                                                    \
+    }                                                                                                              \
+  } while (0)
+#else
+#define A3D_DEV_CHECK(cond) ((void)0)
+#endif
+
 // Launch a kernel of the decoder chain with programmatic stream serialization (see ptx::pdl_sync): the kernel's
 // prologue overlaps the tail of the previous kernel in the stream.  A3D_PDL=0 turns the attribute off (plain
 // stream-ordered launches; griddepcontrol.* are then no-ops).  `cluster` > 1 adds a run-time cluster dimension (kernels

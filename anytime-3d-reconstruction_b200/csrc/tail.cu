@@ -88,6 +88,7 @@ tail_simt_kernel(const uint16_t* __restrict__ a4, const float* __restrict__ w5 /
     const int od = 2 * jd + pd, oh = 2 * jh + ph, ow = 2 * jw;
     const size_t v = ((size_t)od * GO + oh) * GO + ow;
     const float m0 = psum[p] * invk, m1 = psum[p + 1] * invk;
+    A3D_DEV_CHECK(v + 1 < (size_t)A3D_VOXELS);
     if (mean_prob) *reinterpret_cast<float2*>(mean_prob + (size_t)b * A3D_VOXELS + v) = make_float2(m0, m1);
     if (target_bits) {
       const uint32_t byte = target_bits[(size_t)b * (A3D_VOXELS / 8) + (v >> 3)];

@@ -188,8 +188,10 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       if (target_bits && fin && (okw[0] || okw[1])) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (okd[q >> 1] && okh[q & 1])
+          if (okd[q >> 1] && okh[q & 1]) {
+            A3D_DEV_CHECK(obj >= 0 && obj < B && (unsigned)(vbase + (q >> 1) * 4096 + (q & 1) * 64 + 1) < (unsigned)A3D_VOXELS);
             tbyte[q] = target_bits[(size_t)obj * (A3D_VOXELS / 8) + ((vbase + (q >> 1) * 4096 + (q & 1) * 64) >> 3)];
+          }
       }
       // running sums over the K samples, [pd][pw] as (ph = 0, ph = 1) pairs; with the sigmoid: sums of tanh(logit / 2)
       uint64_t psum[4];
@@ -280,6 +282,7 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           packed = __reduce_add_sync(0xffffffffu, packed);
           if (lane < 3) {
             const uint32_t f = (packed >> (10 * lane)) & 1023u;
+            A3D_DEV_CHECK(obj >= 0 && obj < B);
             if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
           }
         }
@@ -301,6 +304,9 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             for (int q = 0; q < 4; ++q) {          // q = pd * 2 + ph; the pw = 0 / 1 outputs are adjacent floats
               if (!(okd[q >> 1] && okh[q & 1])) continue;
               float* dst = base + (q >> 1) * 4096 + (q & 1) * 64;
+              A3D_DEV_CHECK(obj < B && (okw[0] ? vbase + (q >> 1) * 4096 + (q & 1) * 64 >= 0 : true) &&
+                            (!(okw[0] || okw[1]) || (unsigned)(vbase + (q >> 1) * 4096 + (q & 1) * 64 + (okw[0] ? 0 : 1)) < (unsigned)A3D_VOXELS) &&
+                            (!okw[1] || vbase + (q >> 1) * 4096 + (q & 1) * 64 + 1 < A3D_VOXELS));
               if (okw[0] && okw[1]) *reinterpret_cast<float2*>(dst) = make_float2(mv[2 * q], mv[2 * q + 1]);
               else if (okw[0]) dst[0] = mv[2 * q];
               else if (okw[1]) dst[1] = mv[2 * q + 1];
@@ -318,7 +324,8 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
             packed = __reduce_add_sync(0xffffffffu, packed);
             if (lane < 3) {
               const uint32_t f = (packed >> (10 * lane)) & 1023u;
-              if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
+              A3D_DEV_CHECK(obj >= 0 && obj < B);
+            if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
             }
           }
         }
@@ -331,6 +338,7 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           for (int ph = 0; ph < 2; ++ph) {
             if (!(okd[pd] && okh[ph] && (okw[0] || okw[1]))) continue;
             const int v0 = vbase + pd * 4096 + ph * 64;     // voxel index of the pw = 0 output; pw = 1 is the next bit
+            A3D_DEV_CHECK(obj < B && (!(okw[0] && okw[1]) || (v0 >= 0 && v0 + 1 < A3D_VOXELS)));
             const uint32_t byte = tbyte[pd * 2 + ph];
             float mpair = 0.f;
 #pragma unroll
@@ -345,6 +353,7 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
                   if (pw == 0) mpair = mval;
                   else *reinterpret_cast<float2*>(mean_prob + (size_t)obj * A3D_VOXELS + v0) = make_float2(mpair, mval);
                 } else {
+                  A3D_DEV_CHECK((unsigned)(v0 + pw) < (unsigned)A3D_VOXELS);
                   mean_prob[(size_t)obj * A3D_VOXELS + v0 + pw] = mval;
                 }
               }
@@ -368,6 +377,7 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
           packed = __reduce_add_sync(0xffffffffu, packed);
           if (lane < 3) {
             const uint32_t f = (packed >> (10 * lane)) & 1023u;
+            A3D_DEV_CHECK(obj >= 0 && obj < B);
             if (f) atomicAdd(counts + obj * 3 + lane, (unsigned long long)f);
           }
         }
