@@ -52,6 +52,7 @@ conv2d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  ptx::pdl_sync();   // programmatic dependent launch: the prologue above overlaps the previous kernel (ptx.cuh)
   constexpr uint32_t idesc = ptx::make_idesc_f16(128, 32, FMT);
   const uint32_t a_lo = ptx::sw128_desc_lo(ptx::smem_u32(&sA[0][0])), b_lo = ptx::sw128_desc_lo(ptx::smem_u32(sB));
   const int wi = tid & ((1 << g.lw) - 1), hi = (tid >> g.lw) & ((1 << g.lh) - 1), ni = tid >> (g.lw + g.lh);
@@ -183,7 +184,7 @@ int launch_conv2d_first_tc(const float* in, const void* w32x32, const float* sca
   const int grid = g.total_tiles < num_sms * 4 ? g.total_tiles : num_sms * 4;
   const uint16_t* w = reinterpret_cast<const uint16_t*>(w32x32);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-#define A3D_FTC(FMT_, ACT_) conv2d_first_tc_kernel<FMT_, ACT_><<<grid, 128, 0, st>>>(in, w, scale, shift, o, g)
+#define A3D_FTC(FMT_, ACT_) A3D_CUDA_OK(launch_chain(conv2d_first_tc_kernel<FMT_, ACT_>, dim3(grid), dim3(128), 0, st, 1, in, w, scale, shift, o, g))
 #define A3D_FTC_ACT(FMT_)                                            \
   switch (act) {                                                     \
     case A3D_ACT_ELU: A3D_FTC(FMT_, A3D_ACT_ELU); break;             \

@@ -88,6 +88,7 @@ conv2d_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();   // programmatic dependent launch: the prologue above overlaps the previous layer (ptx.cuh)
 
   if (warp == 0 || warp == 3) {
     // ===================================================== TMA producers (even / odd K steps), one pair per CTA
@@ -259,19 +260,8 @@ int launch_act(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const fl
                const Conv2dGeom& g, int act, int n_cl, cudaStream_t st) {
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_cl * 2);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    A3D_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, reinterpret_cast<uint16_t*>(out), scale, shift, g));
+    A3D_CUDA_OK(launch_chain(kern, dim3(n_cl * 2), dim3(kThreads), SMEM_BYTES, st, 2, ta, tw,
+                             reinterpret_cast<uint16_t*>(out), scale, shift, g));
     return A3D_OK;
   };
   switch (act) {

@@ -139,6 +139,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();   // programmatic dependent launch: the prologue above overlaps the previous layer (ptx.cuh)
 
   if (warp == 0 || warp == 3) {
     // ===================================================== TMA producers (two converged warps, elected-lane issue): warp 0
@@ -497,8 +498,7 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const flo
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(ta, tw, out, scale, shift, g);
-    A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, ta, tw, out, scale, shift, g));
     return A3D_OK;
   };
   switch (act) {

@@ -85,6 +85,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_sync();   // programmatic dependent launch: the prologue above overlaps the previous layer (ptx.cuh)
 
   if (warp == 0 || warp == 3) {
     // ===================================================== TMA producers: warp 0 feeds the even K steps, warp 3 the odd ones
@@ -284,6 +285,7 @@ conv3d_first_tc_kernel(const float* __restrict__ in, const uint16_t* __restrict_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  ptx::pdl_sync();   // programmatic dependent launch: the prologue above overlaps the previous kernel (ptx.cuh)
   constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, FMT);
   const uint32_t a_lo = ptx::sw128_desc_lo(ptx::smem_u32(sA)), b_lo = ptx::sw128_desc_lo(ptx::smem_u32(sB));
   const int G = Gin >> 1;                       // output grid
@@ -378,8 +380,7 @@ int launch_act(const CUtensorMap& ta, const CUtensorMap& tw, void* out, const fl
                const Conv3dGeom& g, int act, int grid, cudaStream_t st) {
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3<BN, MT>::SMEM_BYTES));
-    kern<<<grid, kThreads, Cfg3<BN, MT>::SMEM_BYTES, st>>>(ta, tw, out, scale, shift, g);
-    A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(kern, dim3(grid), dim3(kThreads), Cfg3<BN, MT>::SMEM_BYTES, st, 1, ta, tw, out, scale, shift, g));
     return A3D_OK;
   };
   switch (act) {
@@ -427,7 +428,7 @@ int launch_conv3d_first_tc(const float* in, const void* w64x64, const float* sca
   const int grid = (int)(tiles < (int64_t)num_sms * 4 ? tiles : (int64_t)num_sms * 4);
   const uint16_t* w = reinterpret_cast<const uint16_t*>(w64x64);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-#define A3D_F3(FMT_, ACT_) conv3d_first_tc_kernel<FMT_, ACT_><<<grid, 128, 0, st>>>(in, w, scale, shift, o, (int)n, Gin, (int)tiles)
+#define A3D_F3(FMT_, ACT_) A3D_CUDA_OK(launch_chain(conv3d_first_tc_kernel<FMT_, ACT_>, dim3(grid), dim3(128), 0, st, 1, in, w, scale, shift, o, (int)n, Gin, (int)tiles))
 #define A3D_F3_ACT(FMT_)                                       \
   switch (act) {                                               \
     case A3D_ACT_ELU: A3D_F3(FMT_, A3D_ACT_ELU); break;        \

@@ -8,6 +8,7 @@
 #include "cvt.cuh"
 #include "epilogue.cuh"
 #include "internal.h"
+#include "ptx.cuh"
 #include "philox.cuh"
 
 namespace a3d {
@@ -101,6 +102,7 @@ conv2d_first_pool_kernel(const float* __restrict__ in, const float* __restrict__
 template <int FMT>
 __global__ void __launch_bounds__(256)
 maxpool2d_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int64_t total, int H, int W, int C) {
+  ptx::pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int cg = C >> 3, Wq = W >> 1, Hq = H >> 1;
@@ -125,6 +127,7 @@ maxpool2d_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, in
 // in [n, HW, C] fp32 -> out [n, C]; thread = (image, channel); reduce_mean sums in index order like a serial loop
 __global__ void __launch_bounds__(128)
 global_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total, int HW, int C, int is_max) {
+  ptx::pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -143,6 +146,7 @@ global_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int64_
 template <int FMT>
 __global__ void __launch_bounds__(256)
 import_kernel(const void* __restrict__ in, int in_is_f32, uint16_t* __restrict__ out, int64_t total, int C, int C_pad) {
+  ptx::pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C_pad);
@@ -156,6 +160,7 @@ import_kernel(const void* __restrict__ in, int in_is_f32, uint16_t* __restrict__
 template <int FMT>
 __global__ void __launch_bounds__(256)
 export_kernel(const uint16_t* __restrict__ in, void* __restrict__ out, int out_is_f32, int64_t total, int C, int C_pad) {
+  ptx::pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(128)
 split_sample_kernel(const float* __restrict__ enc_out, int64_t n, int D, int out_stride, float clip, int seed_enable,
                     uint64_t seed, uint64_t obj_offset, float* __restrict__ mean, float* __restrict__ logvar,
                     float* __restrict__ z) {
+  ptx::pdl_sync();
   const int nq = (D + 3) >> 2;
   const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (i >= n * nq) return;
@@ -196,6 +202,7 @@ split_sample_kernel(const float* __restrict__ enc_out, int64_t n, int D, int out
 }
 
 __global__ void __launch_bounds__(256) sigmoid_kernel(float* __restrict__ x, int64_t n) {
+  ptx::pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) x[i] = 1.f / (1.f + __expf(-x[i]));
 }
@@ -204,8 +211,7 @@ __global__ void __launch_bounds__(256) sigmoid_kernel(float* __restrict__ x, int
 
 int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st, int64_t* launches) {
   if (n <= 0) return A3D_OK;
-  sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
-  A3D_CUDA_OK(cudaGetLastError());
+  A3D_CUDA_OK(launch_chain(sigmoid_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 1, x, n));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -241,10 +247,9 @@ int launch_maxpool2d(const void* in, void* out, int64_t n, int H, int W, int C, 
   const int64_t total = n * (H / 2) * (W / 2) * (C / 8);
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (fmt == A3D_DTYPE_F16)
-    maxpool2d_kernel<A3D_DTYPE_F16><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, total, H, W, C);
+    A3D_CUDA_OK(launch_chain(maxpool2d_kernel<A3D_DTYPE_F16>, dim3(grid), dim3(256), 0, st, 1, (const uint16_t*)in, (uint16_t*)out, total, H, W, C));
   else
-    maxpool2d_kernel<A3D_DTYPE_BF16><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, total, H, W, C);
-  A3D_CUDA_OK(cudaGetLastError());
+    A3D_CUDA_OK(launch_chain(maxpool2d_kernel<A3D_DTYPE_BF16>, dim3(grid), dim3(256), 0, st, 1, (const uint16_t*)in, (uint16_t*)out, total, H, W, C));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -253,8 +258,7 @@ int launch_global_pool(const float* in, float* out, int64_t n, int HW, int C, in
                        int64_t* launches) {
   if (n <= 0) return A3D_OK;
   const int64_t total = n * C;
-  global_pool_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(in, out, total, HW, C, is_max);
-  A3D_CUDA_OK(cudaGetLastError());
+  A3D_CUDA_OK(launch_chain(global_pool_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, 1, in, out, total, HW, C, is_max));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -263,6 +267,7 @@ int launch_global_pool(const float* in, float* out, int64_t n, int HW, int C, in
 // device so that the host -> device copy carries 1 byte per sample instead of 4): 16 bytes in, 64 bytes out per thread
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
                                                         int64_t total, float scale) {
+  ptx::pdl_sync();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
   if (i + 16 <= total) {
     const uint4 v = *reinterpret_cast<const uint4*>(in + i);
@@ -280,8 +285,7 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restric
 int launch_u8_to_f32(const uint8_t* in, float* out, int64_t total, float scale, cudaStream_t st, int64_t* launches) {
   if (total <= 0) return A3D_OK;
   const int64_t threads = (total + 15) / 16;
-  u8_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out, total, scale);
-  A3D_CUDA_OK(cudaGetLastError());
+  A3D_CUDA_OK(launch_chain(u8_to_f32_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, 1, in, out, total, scale));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -291,9 +295,8 @@ int launch_import_nhwc(const void* in, int in_is_f32, void* out, int64_t pixels,
   if (pixels <= 0) return A3D_OK;
   const int64_t total = pixels * C_pad;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (fmt == A3D_DTYPE_F16) import_kernel<A3D_DTYPE_F16><<<grid, 256, 0, st>>>(in, in_is_f32, (uint16_t*)out, total, C, C_pad);
-  else import_kernel<A3D_DTYPE_BF16><<<grid, 256, 0, st>>>(in, in_is_f32, (uint16_t*)out, total, C, C_pad);
-  A3D_CUDA_OK(cudaGetLastError());
+  if (fmt == A3D_DTYPE_F16) A3D_CUDA_OK(launch_chain(import_kernel<A3D_DTYPE_F16>, dim3(grid), dim3(256), 0, st, 1, in, in_is_f32, (uint16_t*)out, total, C, C_pad));
+  else A3D_CUDA_OK(launch_chain(import_kernel<A3D_DTYPE_BF16>, dim3(grid), dim3(256), 0, st, 1, in, in_is_f32, (uint16_t*)out, total, C, C_pad));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -303,9 +306,8 @@ int launch_export_nhwc(const void* in, void* out, int out_is_f32, int64_t pixels
   if (pixels <= 0) return A3D_OK;
   const int64_t total = pixels * C;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (fmt == A3D_DTYPE_F16) export_kernel<A3D_DTYPE_F16><<<grid, 256, 0, st>>>((const uint16_t*)in, out, out_is_f32, total, C, C_pad);
-  else export_kernel<A3D_DTYPE_BF16><<<grid, 256, 0, st>>>((const uint16_t*)in, out, out_is_f32, total, C, C_pad);
-  A3D_CUDA_OK(cudaGetLastError());
+  if (fmt == A3D_DTYPE_F16) A3D_CUDA_OK(launch_chain(export_kernel<A3D_DTYPE_F16>, dim3(grid), dim3(256), 0, st, 1, (const uint16_t*)in, out, out_is_f32, total, C, C_pad));
+  else A3D_CUDA_OK(launch_chain(export_kernel<A3D_DTYPE_BF16>, dim3(grid), dim3(256), 0, st, 1, (const uint16_t*)in, out, out_is_f32, total, C, C_pad));
   if (launches) ++*launches;
   return A3D_OK;
 }
@@ -315,9 +317,8 @@ int launch_split_sample(const float* enc_out, int64_t n, int D, int out_stride, 
                         int64_t* launches) {
   if (n <= 0) return A3D_OK;
   const int64_t total = n * ((D + 3) / 4);
-  split_sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(enc_out, n, D, out_stride, clip, seed_enable, seed,
-                                                                        obj_offset, mean, logvar, z);
-  A3D_CUDA_OK(cudaGetLastError());
+  A3D_CUDA_OK(launch_chain(split_sample_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, 1, enc_out, n, D, out_stride,
+                           clip, seed_enable, seed, obj_offset, mean, logvar, z));
   if (launches) ++*launches;
   return A3D_OK;
 }
