@@ -104,10 +104,10 @@ def synth(rank: int, seed: int = 1235):
 
 
 class ClockSampler:
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_id: str):
         self.proc = None
         self.lines = []
-        self.gpu = gpu_index
+        self.gpu = gpu_id            # UUID ("GPU-...") or index as nvidia-smi -i takes it
 
     def start(self):
         # started BEFORE the warm-up steps (nvidia-smi needs ~1 s to come up); stop(t0, t1) keeps only the samples whose
@@ -155,7 +155,7 @@ class ClockSampler:
                     reasons.add(nm)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'power_w_median': float(np.median(pw)) if pw else None, 'reasons': sorted(reasons),
-                'samples_in_timed_region': len(sm), 'samples': n_all}
+                'samples_in_timed_region': len(sm), 'samples': n_all, 'gpu': self.gpu}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
@@ -560,7 +560,12 @@ def _main(args, saved_stdout):
             ms = float(t.item())
         return ms, acc
 
-    sampler = ClockSampler(local_rank)
+    # nvidia-smi numbers the physical GPUs of the box; CUDA's index is relative to CUDA_VISIBLE_DEVICES: address by UUID
+    try:
+        gpu_id = 'GPU-' + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:   # noqa: BLE001
+        gpu_id = str(local_rank)
+    sampler = ClockSampler(gpu_id)
     if rank == 0:
         sampler.start()
     warm = torch.zeros(3, dtype=torch.int64, device=dev)
