@@ -87,6 +87,7 @@ SIGNATURES = {
                                         C.c_void_p]),
     'a3d_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int64]),
     'a3d_debug_read_layer': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]),
+    'a3d_debug_time_tail': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     'a3d_launch_count': (C.c_int64, [C.c_void_p]),
     'a3d_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'a3d_stage_times_ms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

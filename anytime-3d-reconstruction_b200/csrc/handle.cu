@@ -929,6 +929,32 @@ int a3d_decode_host(a3d_handle* h, const float* z_host, int64_t n, void* out_hos
   return A3D_OK;
 }
 
+int a3d_debug_time_tail(a3d_handle* h, int64_t B, int K, const uint8_t* target_bits_dev, int64_t* counts_dev, int reps,
+                        float* ms_per_launch, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (B < 1 || K < 1 || reps < 1 || !target_bits_dev || !counts_dev || !ms_per_launch || B * K > h->last_chunk_n) {
+    set_error("a3d_debug_time_tail: bad arguments (B * K must not exceed the %lld decodes of the last chunk)",
+              (long long)h->last_chunk_n);
+    return A3D_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  A3D_CUDA_OK(cudaMemsetAsync(counts_dev, 0, (size_t)B * 3 * sizeof(int64_t), st));
+  for (int i = 0; i < 2; ++i)   // warm-up
+    if ((rc = sticky(h, run_tail(h, B, K, target_bits_dev, 0.5f, reinterpret_cast<unsigned long long*>(counts_dev), nullptr,
+                                 0.f, nullptr, st)))) return rc;
+  A3D_CUDA_OK(cudaEventRecord(h->ev[0], st));
+  for (int i = 0; i < reps; ++i)
+    if ((rc = sticky(h, run_tail(h, B, K, target_bits_dev, 0.5f, reinterpret_cast<unsigned long long*>(counts_dev), nullptr,
+                                 0.f, nullptr, st)))) return rc;
+  A3D_CUDA_OK(cudaEventRecord(h->ev[1], st));
+  A3D_CUDA_OK(cudaEventSynchronize(h->ev[1]));
+  float ms = 0.f;
+  A3D_CUDA_OK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  *ms_per_launch = ms / (float)reps;
+  return A3D_OK;
+}
+
 int a3d_debug_read_layer(a3d_handle* h, int layer, int64_t n, float* host, size_t nbytes) {
   int rc = check_handle(h);
   if (rc) return rc;

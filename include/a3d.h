@@ -160,6 +160,14 @@ size_t a3d_workspace_bytes(const a3d_handle* h, int64_t n);
  * outputs, NDHWC) of the most recent chunk to `host` as fp32.  Synchronous. */
 int a3d_debug_read_layer(a3d_handle* h, int layer, int64_t n, float* host, size_t nbytes);
 
+/* Diagnostics for roofline studies: run ONLY the fused tail `reps` times on the 32^3 x 64 activations the most recent
+ * chunk left in the arena (B objects x K samples, B * K <= that chunk's decodes), timed with CUDA events on `stream`;
+ * *ms_per_launch receives the average.  counts_dev [B,3] is zeroed first and accumulates over the repetitions.
+ * Synchronous.  (Inside a step the tail shares the GPU's power budget with the tensor-bound layers; alone it shows what
+ * the kernel and the memory system do at the clock a memory-bound kernel is given.) */
+int a3d_debug_time_tail(a3d_handle* h, int64_t B, int K, const uint8_t* target_bits_dev, int64_t* counts_dev, int reps,
+                        float* ms_per_launch, void* stream);
+
 /* Kernel launches issued by this handle since creation (what bench.py reports as gpu_launches). */
 int64_t a3d_launch_count(const a3d_handle* h);
 
