@@ -36,9 +36,17 @@ namespace a3d {
 
 namespace {
 
-template <int CIN_, int COUT_, int WIN_, int PAIR_>
+template <int CIN_, int COUT_, int WIN_, int PAIR_, bool HP_ = false>
 struct Cfg {
   static constexpr int CIN = CIN_, COUT = COUT_, WIN = WIN_, PAIR = PAIR_;
+  // HP (PAIR = 2 only): the two CTAs of a pair take the input rows h = 2 hp and 2 hp + 1 of the SAME decode block instead of
+  // the same row of two decode blocks -- for calls with an odd / single decode block (32 latents are ONE block of the
+  // 512->256 layer), where the decode pairing runs half empty and the single-CTA kernel is bound by streaming every
+  // weight tile to every SM.  The two rows see different h borders, so no (sd, sh) step is skipped in h: the row outside
+  // the grid arrives as a zero tile (TMA out-of-bounds fill), 1 / (2 W) of the MACs.
+  static constexpr bool HP = HP_;
+  static_assert(!HP_ || PAIR_ == 2, "HP pairs two CTAs");
+  static constexpr int POS_PER_BLOCK = HP_ ? WIN_ * WIN_ / 2 : WIN_ * WIN_;   // schedule positions per decode-block group
   static constexpr int NT = 128 / WIN;                    // decodes per unit
   static constexpr bool PWB = (COUT <= 128);              // both pw parities in one unit
   static constexpr int NPAR = PWB ? 4 : 8;                // parity classes per position
@@ -66,6 +74,49 @@ struct Cfg {
 constexpr int kEpiWarps = 8;                 // warps 0..7, 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kWarpAlloc = 8, kWarpTma = 10, kWarpMma = 11;
+
+// Unit schedule of a CTA (pair).  A unit is (parity class, position) with position = (decode-block group, d, h).  The
+// grid is split into `reg` regular workers (a multiple of the class count: worker w owns class w % NPAR for the whole
+// launch -- the weight tiles of a class stay hot in L2 -- and walks its positions with stride reg / NPAR) and up to
+// NPAR - 1 helpers: 148 SMs are 74 pairs = 72 regular + 2 helpers.  Helper e finishes the positions [pos_reg, n_pos) of
+// the classes e, e + H, e + 2H, ... one class after the other; pos_reg balances both kinds of worker.  With the plain
+// round-robin walk the two left-over pairs (4 SMs) idled; letting EVERY worker rotate through the classes was slower.
+struct Walk {
+  int npar, n_pos, pos_reg, reg, helpers;
+  __device__ __forceinline__ int count(int worker) const {
+    if (worker < reg) { const int r = reg / npar, p0 = worker / npar; return p0 < pos_reg ? (pos_reg - p0 + r - 1) / r : 0; }
+    return helpers > 0 ? (npar / helpers) * (n_pos - pos_reg) : 0;
+  }
+  // k-th unit of `worker`: class and position
+  __device__ __forceinline__ void unit(int worker, int k, int& par, int& pos) const {
+    if (worker < reg) {
+      par = worker % npar;
+      pos = worker / npar + k * (reg / npar);
+    } else {
+      const int e = worker - reg, tail = n_pos - pos_reg;
+      par = e + (k / tail) * helpers;
+      pos = pos_reg + k % tail;
+    }
+  }
+};
+
+__host__ __device__ inline Walk make_walk(int npar, int n_pos, int workers) {
+  Walk w;
+  w.npar = npar;
+  w.n_pos = n_pos;
+  w.reg = workers - workers % npar;
+  w.helpers = workers - w.reg;
+  if (w.helpers > 0 && (npar % w.helpers != 0 || n_pos < 4 * (w.reg / npar))) w.helpers = 0;
+  w.pos_reg = n_pos;
+  if (w.helpers > 0) {
+    // regular: pos_reg / r units each; helper: (npar / helpers) * (n_pos - pos_reg)
+    const long long r = w.reg / npar, c = npar / w.helpers;
+    w.pos_reg = (int)(((long long)n_pos * c * r + c * r) / (c * r + 1));
+    if (w.pos_reg > n_pos) w.pos_reg = n_pos;
+    if (w.pos_reg == n_pos) w.helpers = 0;
+  }
+  return w;
+}
 
 template <class C, int FMT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -96,8 +147,21 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   const int rank = (PAIR == 2) ? (int)ptx::cluster_ctarank() : 0;
   const int cl_id = blockIdx.x / PAIR;           // cluster (or CTA) index
   const int n_cl = gridDim.x / PAIR;
-  const int nb_groups = (n_blocks + PAIR - 1) / PAIR;
-  const int total_units = nb_groups * WIN * WIN * C::NPAR;
+  const int nb_groups = C::HP ? n_blocks : (n_blocks + PAIR - 1) / PAIR;
+  const Walk walk = make_walk(C::NPAR, nb_groups * C::POS_PER_BLOCK, n_cl);
+  // position -> (input row h, depth d, decode block) of THIS CTA
+  auto decode_pos = [&](int pos, int& h, int& d, int& nb) {
+    if constexpr (C::HP) {
+      h = 2 * (pos % (WIN / 2)) + rank;
+      d = (pos / (WIN / 2)) % WIN;
+      nb = pos / C::POS_PER_BLOCK;
+    } else {
+      h = pos % WIN;
+      d = (pos / WIN) % WIN;
+      nb = (pos / (WIN * WIN)) * PAIR + rank;
+    }
+  };
+  const int my_units = walk.count(cl_id);
 
   if (warp == kWarpTma && lane == 0) {
     ptx::prefetch_tmap(&tmap_act);
@@ -130,10 +194,11 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     // ===================================================== TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
-      for (int u = cl_id; u < total_units; u += n_cl) {
-        const int par = u % C::NPAR;
-        const int pos = u / C::NPAR;
-        const int h = pos % WIN, d = (pos / WIN) % WIN, nb = (pos / (WIN * WIN)) * PAIR + rank;
+      for (int k = 0; k < my_units; ++k) {
+        int par, pos;
+        walk.unit(cl_id, k, par, pos);
+        int h, d, nb;
+        decode_pos(pos, h, d, nb);
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
         const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
         for (int sd = 0; sd < 2; ++sd) {
@@ -141,7 +206,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           if (id < 0 || id >= WIN) continue;
           for (int sh = 0; sh < 2; ++sh) {
             const int ih = h + sh - 1 + ph;
-            if (ih < 0 || ih >= WIN) continue;
+            if (!C::HP && (ih < 0 || ih >= WIN)) continue;     // HP: a row outside the grid is a zero tile (TMA fill)
             for (int c = 0; c < C::CHUNKS; ++c) {
               const int as = a_it % C::A_STAGES;
               ptx::mbar_wait(&a_empty[as], ((a_it / C::A_STAGES) & 1) ^ 1);
@@ -186,10 +251,11 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       constexpr uint32_t idesc_half = ptx::make_idesc_f16(MM, COUT, FMT);
       const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
       const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
-      for (int u = cl_id; u < total_units; u += n_cl, ++unit_it) {
-        const int par = u % C::NPAR;
-        const int pos = u / C::NPAR;
-        const int h = pos % WIN, d = (pos / WIN) % WIN;
+      for (int k = 0; k < my_units; ++k, ++unit_it) {
+        int par, pos;
+        walk.unit(cl_id, k, par, pos);
+        int h, d, nb_unused;
+        decode_pos(pos, h, d, nb_unused);
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
         const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
         const int pw = par & 1;  // only meaningful when !PWB
@@ -203,7 +269,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           if (id < 0 || id >= WIN) continue;
           for (int sh = 0; sh < 2; ++sh) {
             const int ih = h + sh - 1 + ph;
-            if (ih < 0 || ih >= WIN) continue;
+            if (!C::HP && (ih < 0 || ih >= WIN)) continue;
             for (int c = 0; c < C::CHUNKS; ++c) {
               const int as = a_it % C::A_STAGES;
               ptx::mbar_wait(&a_full[as], (a_it / C::A_STAGES) & 1);
@@ -272,10 +338,11 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     constexpr int NCOLS = NACC / 2;                    // columns per warp
     uint8_t* stage = smem_o + e * 4096;                // this warp's 32 rows x 128 B staging tile
     uint32_t unit_it = 0;
-    for (int u = cl_id; u < total_units; u += n_cl, ++unit_it) {
-      const int par = u % C::NPAR;
-      const int pos = u / C::NPAR;
-      const int h = pos % WIN, d = (pos / WIN) % WIN, nb = (pos / (WIN * WIN)) * PAIR + rank;
+    for (int k = 0; k < my_units; ++k, ++unit_it) {
+      int par, pos;
+      walk.unit(cl_id, k, par, pos);
+      int h, d, nb;
+      decode_pos(pos, h, d, nb);
       const int pd = C::PWB ? (par >> 1) : (par >> 2);
       const int ph = C::PWB ? (par & 1) : ((par >> 1) & 1);
       const int buf = unit_it % C::NBUF;
@@ -355,12 +422,15 @@ int launch_cfg(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fm
                cudaStream_t st) {
   constexpr int PAIR = C::PAIR;
   const int n_blocks = (int)((n + C::NT - 1) / C::NT);
-  const int total_units = ((n_blocks + PAIR - 1) / PAIR) * C::WIN * C::WIN * C::NPAR;
+  const int n_pos = (C::HP ? n_blocks : (n_blocks + PAIR - 1) / PAIR) * C::POS_PER_BLOCK;   // >= 8 >= NPAR
   int n_cl = num_sms / PAIR;
-  if (n_cl > total_units) n_cl = total_units;
-  // keep the parity class of a CTA (pair) fixed across its units (weights of one class stay hot in L2)
-  if (n_cl > C::NPAR) n_cl -= n_cl % C::NPAR;
-  if (n_cl < 1) n_cl = 1;
+  if (n_cl > n_pos * C::NPAR) n_cl = n_pos * C::NPAR;
+  // regular workers keep their parity class for the whole launch, the left-over workers help (see Walk); when helping
+  // does not pay (tiny launches) they are not launched at all
+  {
+    const Walk w = make_walk(C::NPAR, n_pos, n_cl);
+    n_cl = w.reg + w.helpers;
+  }
   const CUtensorMap& tw = (PAIR == 2) ? L.tmap_wgt64 : L.tmap_wgt;
   auto launch = [&](auto kern) -> int {
     A3D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -394,34 +464,48 @@ size_t convt_tc_smem_bytes(int cin, int cout, int win) {
   return 0;
 }
 
-// PAIR = 2 shares every weight tile between two decode blocks but needs an even number of blocks and halves the number
-// of schedulable workers; for small calls (the reference's 32- and 72-latent decoder calls) the single-CTA kernel wins
-// whenever it saves a scheduling round.  `slowdown` = measured unit time of PAIR = 1 relative to PAIR = 2 per row of work.
-template <class C2, class C1>
-bool prefer_single(int64_t n, int num_sms, float slowdown) {
+// Variant choice per call size.  The decode pairing (PAIR = 2) shares every weight tile between two decode blocks: best
+// for the large launches, but it needs an even number of blocks and halves the number of schedulable workers.  For small
+// calls (the reference's 32- and 72-latent decoder calls) the h pairing (two input rows of ONE block per pair) or the
+// single-CTA kernel saves scheduling rounds.  Cost = units of the busiest worker x relative unit time: 1 for the decode
+// pairing, 1 + 1 / (2 W) for the h pairing (its zero rows), `single_cost` for the single-CTA kernel (measured: it
+// streams every weight tile to every SM and is bound by the L2 -> SM fabric on the 512->256 layer).
+enum { kVarPair = 0, kVarHp = 1, kVarSingle = 2 };
+template <class C2>
+int pick_variant(int64_t n, int num_sms, float single_cost) {
   const int nb = (int)((n + C2::NT - 1) / C2::NT);
-  auto rounds = [](int units, int workers) { return (units + workers - 1) / workers; };
-  int w2 = num_sms / 2, w1 = num_sms;
-  if (w2 > C2::NPAR) w2 -= w2 % C2::NPAR;
-  if (w1 > C1::NPAR) w1 -= w1 % C1::NPAR;
-  const int u2 = ((nb + 1) / 2) * C2::WIN * C2::WIN * C2::NPAR, u1 = nb * C1::WIN * C1::WIN * C1::NPAR;
-  return rounds(u1, w1 < 1 ? 1 : w1) * slowdown < (float)rounds(u2, w2 < 1 ? 1 : w2);
+  auto rounds = [](int npar, int n_pos, int workers) {      // units of the busiest worker
+    if (workers > n_pos * npar) workers = n_pos * npar;
+    const Walk w = make_walk(npar, n_pos, workers);
+    const int r = w.reg / npar;
+    const int reg_rounds = (w.pos_reg + r - 1) / r;
+    const int help_rounds = w.helpers > 0 ? (npar / w.helpers) * (n_pos - w.pos_reg) : 0;
+    return reg_rounds > help_rounds ? reg_rounds : help_rounds;
+  };
+  constexpr int WW = C2::WIN * C2::WIN;
+  const float c_pair = (float)rounds(C2::NPAR, ((nb + 1) / 2) * WW, num_sms / 2);
+  const float c_hp = rounds(C2::NPAR, nb * WW / 2, num_sms / 2) * (1.f + 0.5f / C2::WIN);
+  const float c_single = rounds(C2::NPAR, nb * WW, num_sms) * single_cost;
+  if (c_pair <= c_hp && c_pair <= c_single) return kVarPair;
+  return c_hp <= c_single ? kVarHp : kVarSingle;
 }
 
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
                        cudaStream_t st, int64_t* launches) {
-  static const int pair_env = getenv("A3D_CONV_PAIR") ? atoi(getenv("A3D_CONV_PAIR")) : 0;   // 1 / 2 force a variant
+  // A3D_CONV_PAIR = 1 / 2 / 3 forces the single-CTA / decode-pair / h-pair variant (diagnostics)
+  static const int pair_env = getenv("A3D_CONV_PAIR") ? atoi(getenv("A3D_CONV_PAIR")) : 0;
+  const int forced = pair_env == 1 ? kVarSingle : pair_env == 2 ? kVarPair : pair_env == 3 ? kVarHp : -1;
   int rc;
   if (L.cin == 512 && L.cout == 256 && L.win == 4) {
-    using C2 = Cfg<512, 256, 4, 2>;
-    using C1 = Cfg<512, 256, 4, 1>;
-    const bool single = pair_env == 1 || (pair_env != 2 && prefer_single<C2, C1>(n, num_sms, 1.3f));
-    rc = single ? launch_cfg<C1>(L, out, n, n_alloc, fmt, act, num_sms, st) : launch_cfg<C2>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    const int v = forced >= 0 ? forced : pick_variant<Cfg<512, 256, 4, 2>>(n, num_sms, 1.6f);
+    rc = v == kVarSingle ? launch_cfg<Cfg<512, 256, 4, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+         : v == kVarHp   ? launch_cfg<Cfg<512, 256, 4, 2, true>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+                         : launch_cfg<Cfg<512, 256, 4, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   } else if (L.cin == 256 && L.cout == 128 && L.win == 8) {
-    using C2 = Cfg<256, 128, 8, 2>;
-    using C1 = Cfg<256, 128, 8, 1>;
-    const bool single = pair_env == 1 || (pair_env != 2 && prefer_single<C2, C1>(n, num_sms, 1.07f));
-    rc = single ? launch_cfg<C1>(L, out, n, n_alloc, fmt, act, num_sms, st) : launch_cfg<C2>(L, out, n, n_alloc, fmt, act, num_sms, st);
+    const int v = forced >= 0 ? forced : pick_variant<Cfg<256, 128, 8, 2>>(n, num_sms, 1.15f);
+    rc = v == kVarSingle ? launch_cfg<Cfg<256, 128, 8, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+         : v == kVarHp   ? launch_cfg<Cfg<256, 128, 8, 2, true>>(L, out, n, n_alloc, fmt, act, num_sms, st)
+                         : launch_cfg<Cfg<256, 128, 8, 2>>(L, out, n, n_alloc, fmt, act, num_sms, st);
   }
   else if (L.cin == 128 && L.cout == 64 && L.win == 16)
     rc = launch_cfg<Cfg<128, 64, 16, 1>>(L, out, n, n_alloc, fmt, act, num_sms, st);
