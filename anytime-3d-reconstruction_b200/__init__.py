@@ -33,7 +33,7 @@ from .encoder3d import Encoder3D, encoder3D
 
 __all__ = ['decoder3D', 'Decoder3D', 'sampling', 'voxelPrecisionRecall', 'voxelPrecisionRecallSweep', 'binary_loss',
            'anytime_eval', 'anytime_eval_host', 'impute', 'getEval', 'pack_targets', 'iou_from_counts', 'shard_range',
-           'nearest_prior', 'pinned_empty',
+           'nearest_prior', 'pinned_empty', 'getPredShapes',
            'allreduce_counts', 'Darknet19', 'head2D', 'image_encoder', 'Encoder2D', 'getEvalImages', 'encoder3D', 'Encoder3D', 'getEvalVoxels']
 
 
@@ -591,6 +591,40 @@ def getEvalVoxels(encoder: Encoder3D, decoder: Decoder3D, inputs, category_vecto
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU plumbing
+def getPredShapes(decoder: Decoder3D, inst_mean, inst_log_var, is_sampling: bool = True, sampling_num: int = 32,
+                  seed: int | None = None, obj_offset: int = 0):
+    """The 3-D shape block of getPred (src/module/nolbo_test.py:167-182) for ALL selected instances in one call:
+    ``is_sampling``: every instance's (mean, logVar) is stacked ``sampling_num`` times, ``sampling`` draws the latents, the
+    decoder runs on all of them and the ``sampling_num`` post-sigmoid grids of an instance are averaged
+    (``tf.reduce_mean(self._decoder(latents, training=False), axis=0)``); otherwise ``decoder(inst_mean)``.
+    The reference loops over the instances (32 decodes per decoder call); here the draws (a3d_sampling), the decodes and
+    the K-sample mean (fused into the tail kernel) of all instances are one launch chain.
+    Returns float32 [N, 64, 64, 64] (numpy in -> numpy out, CUDA tensor in -> CUDA tensor out); N = 0 gives an empty array."""
+    torch = _require_cuda()
+    is_np = not isinstance(inst_mean, torch.Tensor)
+    dev = decoder.device
+    mean = _as_dev_f32(inst_mean, torch, dev).reshape(-1, decoder.input_dim)
+    n = mean.shape[0]
+    if n == 0:
+        out = torch.empty((0, 64, 64, 64), dtype=torch.float32, device=dev)
+        return out.cpu().numpy() if is_np else out
+    if not is_sampling:
+        out = decoder(mean).reshape(n, 64, 64, 64)
+        return out.cpu().numpy() if is_np else out
+    logvar = _as_dev_f32(inst_log_var, torch, dev).reshape(-1, decoder.input_dim)
+    if logvar.shape != mean.shape:
+        raise ValueError('inst_mean and inst_log_var must have the same shape')
+    K = int(sampling_num)
+    zc = sampling(mean.repeat_interleave(K, dim=0), logvar.repeat_interleave(K, dim=0), seed=seed, decoder=decoder,
+                  obj_offset=obj_offset * K).reshape(n, K, decoder.input_dim)
+    grid = torch.empty((n, 64, 64, 64, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(decoder.device_index):
+        _capi.check(decoder._lib.a3d_anytime_eval(decoder._h, zc.data_ptr(), n, K, 0, 0.5, 0, grid.data_ptr(),
+                                                  _stream_ptr(torch)), 'a3d_anytime_eval')
+    out = grid.reshape(n, 64, 64, 64)
+    return out.cpu().numpy() if is_np else out
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous object shard [lo, hi) of rank ``rank``: objects (with all their K samples) never cross GPUs."""
     per = -(-n // world)

@@ -233,6 +233,7 @@ def parity_spot(a3d, dec, st, ws, z, mask, mu, bits_rows, seed, obj_offset, pick
     objects with their global object ids (same Philox draws), the oracle decodes the same completed latents."""
     from oracle import anytime_ref as ar
     out = {'objects': [int(p) for p in pick], 'K': K, 'max_dp': 0.0, 'flips': 0, 'voxels': 0, 'dcounts': 0}
+    got_c, ref_c = [], []
     for p in pick:
         r = a3d.anytime_eval(dec, z[p:p + 1], mask[p:p + 1], mu, bits_rows[p:p + 1], K=K, seed=seed, fill='prior_sample',
                              obj_offset=obj_offset + p, return_grid=True)
@@ -245,9 +246,16 @@ def parity_spot(a3d, dec, st, ws, z, mask, mu, bits_rows, seed, obj_offset, pick
         out['flips'] += int(((mp >= 0.5) != (ref_mp >= 0.5)).sum())
         out['voxels'] += int(mp.size)
         out['dcounts'] += int(np.abs(cnt - ref_cnt).sum())
+        got_c.append(cnt[0].astype(np.float64))
+        ref_c.append(np.asarray(ref_cnt)[0].astype(np.float64))
         if full_counts is not None:      # the counts-only call of the timed batch: same integers up to threshold ties
             out['dcounts_vs_timed_batch'] = out.get('dcounts_vs_timed_batch', 0) + int(np.abs(full_counts[p] - cnt[0]).sum())
     out['flips_pct'] = 100.0 * out['flips'] / max(out['voxels'], 1)
+    # IoU = TP / (TP + FP + FN): mean over the spot objects and the global ratio, GPU minus oracle
+    g, r = np.array(got_c), np.array(ref_c)
+    iou = lambda c: c[:, 0] / np.maximum(c.sum(1), 1.0)
+    out['iou_delta_mean'] = float(iou(g).mean() - iou(r).mean())
+    out['iou_delta_global'] = float(g[:, 0].sum() / max(g.sum(), 1.0) - r[:, 0].sum() / max(r.sum(), 1.0))
     out['ok'] = bool(out['max_dp'] < 1e-2 and out['flips_pct'] < 0.1)
     return out
 
@@ -656,6 +664,8 @@ def _main(args, saved_stdout):
                     'max_dp': max(a['max_dp'], b['max_dp']), 'flips': a['flips'] + b['flips'],
                     'flips_pct': 100.0 * (a['flips'] + b['flips']) / (a['voxels'] + b['voxels']),
                     'dcounts': a['dcounts'] + b['dcounts'],
+                    'iou_delta_mean': 0.5 * (a['iou_delta_mean'] + b['iou_delta_mean']),
+                    'iou_delta_per_object': [a['iou_delta_mean'], b['iou_delta_mean']],
                     'dcounts_vs_timed_batch': a['dcounts_vs_timed_batch'] + b['dcounts_vs_timed_batch'],
                     'ok': a['ok'] and b['ok']}
 

@@ -59,6 +59,31 @@ def test_k32_samples_of_one_object(a3d_mod, trained):
     assert np.abs(grids.mean(0, dtype=np.float64) - ref_mp[0]).max() < PROB_TOL
 
 
+def test_getPredShapes_all_instances_in_one_call(a3d_mod, trained):
+    """a3d.getPredShapes = the 3-D shape block of nolbo_test.getPred (:167-182) for all selected instances at once: the
+    same draws as `sampling` row by row, the mean of the 32 grids of every instance against the oracle, the
+    is_sampling=False branch (decoder(inst_mean)), the empty selection, numpy in -> numpy out."""
+    dec = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=64)       # 3 instances x 32 draws = 96 decodes: two chunks
+    dec.set_weights(trained)
+    rng = np.random.default_rng(321)
+    mean = dr.round_bf16(rng.standard_normal((3, 64)).astype(np.float32))
+    logvar = rng.uniform(-3.0, -1.0, (3, 64)).astype(np.float32)
+    got = a3d_mod.getPredShapes(dec, mean, logvar, is_sampling=True, sampling_num=32, seed=5)
+    assert isinstance(got, np.ndarray) and got.shape == (3, 64, 64, 64) and got.dtype == np.float32
+    z = a3d_mod.sampling(np.repeat(mean, 32, 0), np.repeat(logvar, 32, 0), seed=5, decoder=dec).reshape(3, 32, 64)
+    eps = ar.philox_normals(5, np.arange(96, dtype=np.uint64), 1, 64)[:, 0]      # row r draws with the k = 0 stream of object r
+    z_ref = ar.sampling(np.repeat(mean, 32, 0), np.repeat(logvar, 32, 0), eps)
+    assert np.abs(z.reshape(96, 64) - z_ref).max() < 2e-5
+    ref_mp, _ = ar.anytime_eval(dr.MODELNET_DECODER, trained, z, ar.make_targets(rng, 3))
+    ref_mp = ref_mp.reshape(3, 64, 64, 64)
+    assert np.abs(got - ref_mp).max() < PROB_TOL
+    assert ((got >= 0.5) != (ref_mp >= 0.5)).mean() < FLIP_TOL
+    plain = a3d_mod.getPredShapes(dec, mean, logvar, is_sampling=False)
+    ref_plain = dr.decoder_forward(dr.MODELNET_DECODER, trained, mean).numpy().reshape(3, 64, 64, 64)
+    assert np.abs(plain - ref_plain).max() < PROB_TOL
+    assert a3d_mod.getPredShapes(dec, np.zeros((0, 64), np.float32), np.zeros((0, 64), np.float32)).shape == (0, 64, 64, 64)
+
+
 def test_anytime_eval_k32_imputed(a3d_mod, trained):
     """The composed path at the reference's sampling_num: 2 objects x K = 32 prior-sample imputations."""
     dec = a3d_mod.decoder3D(dr.MODELNET_DECODER, max_chunk=64)
