@@ -411,6 +411,15 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       }
       tmem_st16_zero(tacc);
       tmem_st16_zero(tacc + 16);
+      // the accumulators are in registers and the columns are zero again: hand the slot back to the MMA warp NOW, before
+      // the BN / ELU / staging / global stores below.  (Releasing it after the stores, as the first version did, put the
+      // latency of the scattered 32-byte-sector stores on the accumulator ring's critical path: with the stores
+      // predicated off the layer ran 15 % faster, with the ELU removed not at all -- profiles/r02_notes.md section 11.)
+      tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      arrive_empty(slot);
+      if (add3) arrive_empty(3);
       if (valid) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {          // two passes of 16 channels through the 1 KB staging tile
@@ -450,11 +459,6 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           __syncwarp();
         }
       }
-      tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      arrive_empty(slot);
-      if (add3) arrive_empty(3);
     };
 
     uint32_t full_par = 0;      // bit s: parity of the number of "slot closed" signals consumed for slot s
