@@ -23,7 +23,8 @@ aux keys     : config 1 (B = 32 / K = 32 single calls), decoder(z) numpy->numpy 
 `oracle/` is used here in three ways only: the timed CPU baseline, the on-box parity spot check, and as the seeded numpy
 generator of the synthetic inputs / random-init weights (no device compute goes through it).
 `cpu_baseline` / `--impl reference`: the torch-CPU-fp32 oracle (the reference itself needs TensorFlow, which is not
-installable offline -- see DESIGN.md) on a bounded sample (40 objects x K = 16), compute only, all host threads.
+installable offline -- see DESIGN.md) on a bounded sample (40 objects x K = 16; the reference arm shrinks its per-step
+sample, never below 8 objects, so that K + W steps end within ~3 minutes), compute only, all host threads.
 """
 from __future__ import annotations
 
@@ -193,7 +194,15 @@ def run_reference(args, rank, world):
     `cpu_baseline` leg of the main arm times."""
     if rank != 0:
         return
-    s = CpuSample(CPU_SAMPLE_OBJECTS)
+    # the whole --steps K --warmup W run must end within a few minutes: a calibration pass on 8 objects gives the host's
+    # seconds per object, the per-step sample is then the cpu_baseline leg's 40 objects, or fewer when K + W steps of 40
+    # would take longer than ~3 minutes (never fewer than 8)
+    cal = CpuSample(8)
+    sec_per_obj = cal.run() / 8.0
+    budget_s = 180.0
+    n_obj = int(budget_s / (max(args.steps + max(args.warmup, 0), 1) * sec_per_obj))
+    n_obj = max(8, min(CPU_SAMPLE_OBJECTS, n_obj))
+    s = CpuSample(n_obj)
     for _ in range(max(args.warmup, 0)):
         s.run()
     secs = [s.run() for _ in range(args.steps)]
