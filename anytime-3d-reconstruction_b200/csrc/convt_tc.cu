@@ -31,6 +31,7 @@
 #include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
+#include "walk.h"
 
 namespace a3d {
 
@@ -74,49 +75,6 @@ struct Cfg {
 constexpr int kEpiWarps = 8;                 // warps 0..7, 2 per scheduler: warps e and e + 4 share a TMEM lane quarter
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kWarpAlloc = 8, kWarpTma = 10, kWarpMma = 11;
-
-// Unit schedule of a CTA (pair).  A unit is (parity class, position) with position = (decode-block group, d, h).  The
-// grid is split into `reg` regular workers (a multiple of the class count: worker w owns class w % NPAR for the whole
-// launch -- the weight tiles of a class stay hot in L2 -- and walks its positions with stride reg / NPAR) and up to
-// NPAR - 1 helpers: 148 SMs are 74 pairs = 72 regular + 2 helpers.  Helper e finishes the positions [pos_reg, n_pos) of
-// the classes e, e + H, e + 2H, ... one class after the other; pos_reg balances both kinds of worker.  With the plain
-// round-robin walk the two left-over pairs (4 SMs) idled; letting EVERY worker rotate through the classes was slower.
-struct Walk {
-  int npar, n_pos, pos_reg, reg, helpers;
-  __device__ __forceinline__ int count(int worker) const {
-    if (worker < reg) { const int r = reg / npar, p0 = worker / npar; return p0 < pos_reg ? (pos_reg - p0 + r - 1) / r : 0; }
-    return helpers > 0 ? (npar / helpers) * (n_pos - pos_reg) : 0;
-  }
-  // k-th unit of `worker`: class and position
-  __device__ __forceinline__ void unit(int worker, int k, int& par, int& pos) const {
-    if (worker < reg) {
-      par = worker % npar;
-      pos = worker / npar + k * (reg / npar);
-    } else {
-      const int e = worker - reg, tail = n_pos - pos_reg;
-      par = e + (k / tail) * helpers;
-      pos = pos_reg + k % tail;
-    }
-  }
-};
-
-__host__ __device__ inline Walk make_walk(int npar, int n_pos, int workers) {
-  Walk w;
-  w.npar = npar;
-  w.n_pos = n_pos;
-  w.reg = workers - workers % npar;
-  w.helpers = workers - w.reg;
-  if (w.helpers > 0 && (npar % w.helpers != 0 || n_pos < 4 * (w.reg / npar))) w.helpers = 0;
-  w.pos_reg = n_pos;
-  if (w.helpers > 0) {
-    // regular: pos_reg / r units each; helper: (npar / helpers) * (n_pos - pos_reg)
-    const long long r = w.reg / npar, c = npar / w.helpers;
-    w.pos_reg = (int)(((long long)n_pos * c * r + c * r) / (c * r + 1));
-    if (w.pos_reg > n_pos) w.pos_reg = n_pos;
-    if (w.pos_reg == n_pos) w.helpers = 0;
-  }
-  return w;
-}
 
 template <class C, int FMT, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
