@@ -31,11 +31,17 @@
 #include "epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
+#include "l4_sched.h"
 
 namespace a3d {
 namespace {
 
-constexpr int COUT = 64, WIN = 16, NT = 8, CHUNKS = 2;
+using l4::Seg;
+using l4::Sched;
+using l4::make_sched;
+using l4::seg_item;
+using l4::item_depth;
+constexpr int COUT = 64, WIN = l4::WIN, NT = 8, CHUNKS = 2;
 constexpr int A_BYTES = (WIN + 2) * NT * 128;   // 18432: rows (h' = -1..16, decode)
 constexpr int A_STAGES = 4;
 constexpr int OUT_STAGE_BYTES = 16 * 1024;      // per epilogue warp: 32 rows x 32 B (16 channels), XOR-swizzled
@@ -65,12 +71,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // start in A, and one that ends in A has drained slot 2 and frees slot 3 first.  Equal consecutive phases are legal (the
 // MMA warp just waits for the drains).
 __device__ __forceinline__ int start_phase(int d) { return (d & 1) ? 2 : 0; }
-
-// Output depth of item t for a class with depth parity pd.  pd = 1 classes run one plane behind (d = t - 1 mod 16):
-// class (pd, .) reads the input planes d + pd - 1 and d + pd, so with this shift ALL FOUR classes working on item t read
-// the same two planes (t - 1, t) at the same time (L2 reuse), and all four have their half-length item (one plane
-// outside the grid) at t = 0 mod 16, which keeps the clusters of an item in step.
-__device__ __forceinline__ int item_depth(int t, int pd) { return (t + (pd ? WIN - 1 : 0)) % WIN; }
 
 // ELU / ReLU / LeakyReLU / identity on a packed pair of fp32 values, then 16-bit pack.  ELU is branch- and
 // predicate-free: max(v, 2^min(v log2e, 0) - 1) equals v for v > 0 (the exponential term is 0) and exp(v) - 1 below
@@ -105,42 +105,6 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Work list of a cluster: up to two segments.  The regular clusters own one parity class for the whole launch and walk
-// the items [0, limit) of that class in rounds of `per` items; the clusters left over after dividing the grid by four
-// help two classes each with the contiguous tail [first, first + count).
-//   Regular cluster cj takes item k * per + (cj + k) % per in round k: neighbouring clusters always work on neighbouring
-// items (they share an activation plane through L2), and the rotation by k walks every cluster through all 16 depths --
-// with the plain stride-`per` walk (per = 18) the half-length border items (one input plane outside the grid) all went to
-// the even-numbered clusters, which then idled 6 % of the launch.
-struct Seg { int q, first, count, per, cj, limit; };   // per > 0: regular (rounds); per == 0: contiguous tail
-struct Sched { Seg s[2]; };
-
-__device__ __forceinline__ int seg_item(const Seg& S, int k) {
-  if (S.per == 0) return S.first + k;
-  const int t = k * S.per + (S.cj + k) % S.per;
-  return t < S.limit ? t : -1;             // only the last round can be incomplete
-}
-
-__device__ __forceinline__ Sched make_sched(int cluster_id, int n_clusters, int n_items) {
-  Sched sc;
-  const int per = n_clusters >> 2;          // regular clusters per class (the launcher passes 4k or 4k + 2 clusters)
-  const int reg = per << 2;
-  sc.s[1] = Seg{0, 0, 0, 0, 0, 0};
-  // With two helper clusters, each helper finishes two classes: the regular clusters of a class walk items [0, n_reg),
-  // the helper the tail [n_reg, n_items); n_reg / per = 2 (n_items - n_reg) balances both kinds of cluster.
-  int n_reg = n_items;
-  if (n_clusters > reg) n_reg = (int)(((long long)n_items * 2 * per + 2 * per) / (2 * per + 1));
-  if (n_reg > n_items) n_reg = n_items;
-  if (cluster_id < reg) {
-    sc.s[0] = Seg{cluster_id & 3, 0, (n_reg + per - 1) / per, per, cluster_id >> 2, n_reg};
-  } else {
-    const int e = cluster_id - reg;         // 0 or 1
-    sc.s[0] = Seg{2 * e, n_reg, n_items - n_reg, 0, 0, n_items};
-    sc.s[1] = Seg{2 * e + 1, n_reg, n_items - n_reg, 0, 0, n_items};
-  }
-  return sc;
 }
 
 template <int FMT, int ACT>
@@ -506,11 +470,7 @@ int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt,
                        int pace_delta, cudaStream_t st, int64_t* launches) {
   const int n_blocks = (int)((n + NT - 1) / NT);
   const int n_items = ((n_blocks + 1) / 2) * WIN;
-  // 4k clusters (k per output-parity class) or 4k + 2: the two left-over clusters help two classes each
-  int n_clusters = num_sms / 2;
-  if ((n_clusters & 3) != 2 || n_items < 64) n_clusters &= ~3;
-  if (n_clusters > 4 * n_items) n_clusters = 4 * n_items;
-  if (n_clusters < 4) n_clusters = 4;
+  const int n_clusters = l4::num_clusters(num_sms, n_items);
   // pacing needs every cluster resident at once (true for a grid of <= num_sms CTAs on an otherwise idle GPU) and only
   // pays when the launch is long enough for the clusters to drift apart
   if (n_items < 8 * (n_clusters / 4) || 2 * n_clusters > num_sms || (pace_delta & 255) <= 0) progress = nullptr;

@@ -64,3 +64,66 @@ def test_walk_schedule_covers_every_unit_exactly_once(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.startswith('OK'), r.stdout
     assert int(r.stdout.split()[1]) > 5000
+
+
+L4_PROGRAM = textwrap.dedent(r'''
+    #include <cstdio>
+    #include <vector>
+    #include "l4_sched.h"
+    using namespace a3d::l4;
+    int main() {
+      long long cases = 0;
+      const int sms_list[] = {8, 16, 132, 144, 148, 160};
+      for (int num_sms : sms_list)
+        for (int n_pairs = 1; n_pairs <= 600; n_pairs = n_pairs < 40 ? n_pairs + 1 : n_pairs * 2 + 1) {
+          const int n_items = n_pairs * WIN;
+          const int n_cl = num_clusters(num_sms, n_items);
+          if (n_cl < 4 || 2 * n_cl > num_sms + 8 || ((n_cl & 3) != 0 && (n_cl & 3) != 2)) { printf("clusters %d %d -> %d\n", num_sms, n_items, n_cl); return 1; }
+          std::vector<int> seen((size_t)4 * n_items, 0);
+          long long total = 0, mx = 0;
+          for (int c = 0; c < n_cl; ++c) {
+            const Sched sc = make_sched(c, n_cl, n_items);
+            long long mine = 0;
+            for (int sg = 0; sg < 2; ++sg) {
+              const Seg S = sc.s[sg];
+              for (int k = 0; k < S.count; ++k) {
+                const int t = seg_item(S, k);
+                if (t < 0) continue;
+                if (t >= n_items || S.q < 0 || S.q > 3) { printf("range %d %d: cluster %d -> q %d t %d\n", num_sms, n_items, c, S.q, t); return 1; }
+                if (seen[(size_t)S.q * n_items + t]++) { printf("twice %d %d: q %d t %d\n", num_sms, n_items, S.q, t); return 1; }
+                const int d = item_depth(t, S.q >> 1);
+                if (d < 0 || d >= WIN) { printf("depth\n"); return 1; }
+                ++mine;
+              }
+            }
+            total += mine;
+            if (mine > mx) mx = mine;
+          }
+          if (total != 4LL * n_items) { printf("coverage %d %d: %lld of %d\n", num_sms, n_items, total, 4 * n_items); return 1; }
+          const double mean = 4.0 * n_items / n_cl;
+          if (mx > mean + 3) { printf("imbalance %d %d: max %lld mean %.1f\n", num_sms, n_items, mx, mean); return 1; }
+          // per class, the depths 0 .. 15 of every decode-block pair appear exactly once (item t <-> (pair t / 16, depth))
+          for (int q = 0; q < 4; ++q) {
+            std::vector<int> dseen((size_t)n_items, 0);
+            for (int t = 0; t < n_items; ++t) dseen[(size_t)(t / WIN) * WIN + item_depth(t, q >> 1)]++;
+            for (int v : dseen) if (v != 1) { printf("depth permutation broken\n"); return 1; }
+          }
+          ++cases;
+        }
+      printf("OK %lld cases\n", cases);
+      return 0;
+    }
+''')
+
+
+def test_l4_item_schedule_covers_every_item_exactly_once(tmp_path):
+    """csrc/l4_sched.h: the 128->64 kernel's clusters (18 regular per parity class with the rotating item walk + 2 helper
+    clusters on 148 SMs; fewer on small launches) execute every (class, decode-block pair, depth) item exactly once."""
+    src = tmp_path / 'l4_test.cpp'
+    src.write_text(L4_PROGRAM)
+    exe = tmp_path / 'l4_test'
+    r = subprocess.run(['g++', '-O1', '-std=c++17', '-I', CSRC, str(src), '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.startswith('OK'), r.stdout
