@@ -154,7 +154,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       uint32_t a_it = 0, b_it = 0;
       for (int k = 0; k < my_units; ++k) {
         int par, pos;
-        walk.unit(cl_id, k, par, pos);
+        if (!walk.unit(cl_id, k, par, pos)) continue;
         int h, d, nb;
         decode_pos(pos, h, d, nb);
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
@@ -209,9 +209,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       constexpr uint32_t idesc_half = ptx::make_idesc_f16(MM, COUT, FMT);
       const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
       const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_b));
-      for (int k = 0; k < my_units; ++k, ++unit_it) {
+      for (int k = 0; k < my_units; ++k) {
         int par, pos;
-        walk.unit(cl_id, k, par, pos);
+        if (!walk.unit(cl_id, k, par, pos)) continue;
         int h, d, nb_unused;
         decode_pos(pos, h, d, nb_unused);
         const int pd = C::PWB ? (par >> 1) : (par >> 2);
@@ -284,6 +284,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
         if (ptx::elect_one()) ptx::umma_commit<PAIR>(&t_full[buf]);  // accumulators complete -> epilogue(s)
         __syncwarp();
+        ++unit_it;
       }
     }
   } else if (warp < kEpiWarps) {
@@ -296,9 +297,9 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     constexpr int NCOLS = NACC / 2;                    // columns per warp
     uint8_t* stage = smem_o + e * 4096;                // this warp's 32 rows x 128 B staging tile
     uint32_t unit_it = 0;
-    for (int k = 0; k < my_units; ++k, ++unit_it) {
+    for (int k = 0; k < my_units; ++k) {
       int par, pos;
-      walk.unit(cl_id, k, par, pos);
+      if (!walk.unit(cl_id, k, par, pos)) continue;
       int h, d, nb;
       decode_pos(pos, h, d, nb);
       const int pd = C::PWB ? (par >> 1) : (par >> 2);
@@ -367,6 +368,7 @@ convt_s2_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
         __syncwarp();
       }
+      ++unit_it;
     }
   }
 

@@ -37,12 +37,22 @@ PROGRAM = textwrap.dedent(r'''
               total += c;
               for (int k = 0; k < c; ++k) {
                 int par = -1, pos = -1;
-                w.unit(id, k, par, pos);
+                if (!w.unit(id, k, par, pos)) { --total; continue; }     // empty slot of the last regular round
                 if (par < 0 || par >= npar || pos < 0 || pos >= n_pos) { printf("range %d %d %d: worker %d k %d -> %d %d\n", npar, n_pos, wk, id, k, par, pos); return 1; }
                 if (seen[(size_t)par * n_pos + pos]++) { printf("twice %d %d %d: %d %d\n", npar, n_pos, wk, par, pos); return 1; }
               }
             }
             if (total != (long long)npar * n_pos) { printf("coverage %d %d %d: %lld\n", npar, n_pos, wk, total); return 1; }
+            // every regular worker visits every residue of the position index modulo its stride within r rounds (the
+            // rotation that spreads the cheap border rows over all workers)
+            if (w.reg >= npar) {
+              const int r = w.reg / npar;
+              if (w.pos_reg >= r * r) {
+                std::vector<int> res(r, 0);
+                for (int k = 0; k < r; ++k) { int par, pos; if (w.unit(0, k, par, pos)) res[pos % r]++; }
+                for (int v : res) if (v != 1) { printf("rotation %d %d %d\n", npar, n_pos, wk); return 1; }
+              }
+            }
             // balance: the busiest worker is within one unit (regular) or one class sweep (helper) of the mean
             const double mean = (double)npar * n_pos / launched;
             if (mx > mean + npar + 1) { printf("imbalance %d %d %d: max %lld mean %.1f\n", npar, n_pos, wk, mx, mean); return 1; }
