@@ -50,3 +50,15 @@ def test_checked_build_traps_on_a_failing_check(checked_lib):
     r = _run({'A3D_LIB': 'liba3d_checked.so', 'A3D_CHECK_SELFTEST': '1'}, 'sanitize_case.py', timeout=300)
     assert r.returncode != 0
     assert 'A3D_DEV_CHECK failed' in r.stdout + r.stderr
+
+
+def test_programmatic_dependent_launch_changes_no_bit():
+    """Every kernel of the chain starts its prologue while its predecessor drains (ptx::pdl_sync); with A3D_PDL=0 the same
+    kernels are launched stream-ordered.  Both must give identical results on the ragged cases: a read of the previous
+    kernel's output before griddepcontrol.wait would show up here."""
+    on = _run({'A3D_LIB': 'liba3d.so', 'A3D_PDL': '1'}, 'checked_cases.py')
+    assert on.returncode == 0, on.stderr[-2000:]
+    off = _run({'A3D_LIB': 'liba3d.so', 'A3D_PDL': '0'}, 'checked_cases.py')
+    assert off.returncode == 0, off.stderr[-2000:]
+    a, b = json.loads(on.stdout.strip().splitlines()[-1]), json.loads(off.stdout.strip().splitlines()[-1])
+    assert len(a) > 150 and a == b
