@@ -451,10 +451,9 @@ int pick_variant(int64_t n, int num_sms, float single_cost) {
 }
 
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
-                       cudaStream_t st, int64_t* launches) {
-  // A3D_CONV_PAIR = 1 / 2 / 3 forces the single-CTA / decode-pair / h-pair variant (diagnostics)
-  static const int pair_env = getenv("A3D_CONV_PAIR") ? atoi(getenv("A3D_CONV_PAIR")) : 0;
-  const int forced = pair_env == 1 ? kVarSingle : pair_env == 2 ? kVarPair : pair_env == 3 ? kVarHp : -1;
+                       int force_variant, cudaStream_t st, int64_t* launches) {
+  // force_variant (A3D_CONV_PAIR, read when the handle is created) = 1 / 2 / 3: single-CTA / decode-pair / h-pair variant
+  const int forced = force_variant == 1 ? kVarSingle : force_variant == 2 ? kVarPair : force_variant == 3 ? kVarHp : -1;
   int rc;
   if (L.cin == 512 && L.cout == 256 && L.win == 4) {
     const int v = forced >= 0 ? forced : pick_variant<Cfg<512, 256, 4, 2>>(n, num_sms, 1.6f);

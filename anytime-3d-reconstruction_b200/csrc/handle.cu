@@ -126,6 +126,8 @@ struct a3d_handle {
   int* d_progress = nullptr; // pacing counters of the w-sweep kernel (one int per cluster)
   int l4_pace = 8;           // sweep steps a cluster may run ahead of its peers (soft pacing, convt_l4_sw.cu);
                              // A3D_L4_PACE=<n> overrides, 0 switches pacing off
+  int conv_variant = 0;      // A3D_CONV_PAIR = 1 / 2 / 3 forces the single-CTA / decode-pair / h-pair variant of the row-unit
+                             // kernel (0: chosen per call size)
   int l4_impl = 0;           // 128->64 layer: 0 = w-sweep 2-CTA kernel (convt_l4_sw.cu, default); A3D_L4_IMPL=generic: the
                              // 1-CTA kernel of the other stride-2 layers (cross-check; same values up to summation order)
 };
@@ -434,7 +436,8 @@ int run_hidden(a3d_handle* h, const float* z_dev, int64_t n, cudaStream_t st) {
       rc = launch_convt_l4_sw(h->conv[li].tmap_act_sw, h->conv[li].tmap_wgt_sw, h->act[li + 2], h->conv[li].scale,
                               h->conv[li].shift, n, h->max_chunk, fmt, act, h->num_sms, h->d_progress, h->l4_pace, st, &h->launches);
     else
-      rc = launch_convt_s2_tc(h->conv[li], h->act[li + 2], n, h->max_chunk, fmt, act, h->num_sms, st, &h->launches);
+      rc = launch_convt_s2_tc(h->conv[li], h->act[li + 2], n, h->max_chunk, fmt, act, h->num_sms, h->conv_variant, st,
+                              &h->launches);
     if (rc) return rc;
     if (h->profiling) cudaEventRecord(h->ev[2 + li], st);
   }
@@ -556,6 +559,7 @@ int a3d_create(const a3d_desc* d, a3d_handle** out) {
   h->max_chunk = d->max_chunk;
   { const char* e = getenv("A3D_L4_IMPL"); h->l4_impl = (e && std::string(e) == "generic") ? 2 : 0; }
   { const char* e = getenv("A3D_L4_PACE"); if (e) h->l4_pace = atoi(e); }
+  { const char* e = getenv("A3D_CONV_PAIR"); if (e) h->conv_variant = atoi(e); }
   if (cudaMalloc(&h->d_progress, convt_l4_sw_progress_bytes()) != cudaSuccess) {
     set_error("allocation of the pacing counters failed");
     a3d_destroy(h);

@@ -111,7 +111,7 @@ int launch_gemm_l1(const CUtensorMap& tmap_a0, const CUtensorMap& tmap_mt, void*
                    const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, cudaStream_t st,
                    int64_t* launches);
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,
-                       cudaStream_t st, int64_t* launches);
+                       int force_variant, cudaStream_t st, int64_t* launches);
 int launch_convt_l4_sw(const CUtensorMap& tmap_act, const CUtensorMap& tmap_wgt, void* out, const float* scale,
                        const float* shift, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms, int* progress,
                        int pace_delta, cudaStream_t st, int64_t* launches);

@@ -44,6 +44,13 @@ def test_checked_build_passes_the_ragged_cases_and_changes_no_bit(checked_lib):
     assert a.pop('lib') == 'liba3d.so' and b.pop('lib') == 'liba3d_checked.so'
     assert len(a) > 150
     assert a == b
+    # the three variants of the row-unit ConvT kernel (single CTA, decode pairing, h pairing; forced per handle through
+    # A3D_CONV_PAIR) only differ in which CTA computes a unit: bit-identical to the per-call choice
+    for forced in ('pair1', 'pair2', 'pair3'):
+        keys = [k for k in a if k.startswith(forced + '/')]
+        assert len(keys) > 20
+        for k in keys:
+            assert a[k] == a['default/' + k.split('/', 1)[1]], k
 
 
 def test_checked_build_traps_on_a_failing_check(checked_lib):

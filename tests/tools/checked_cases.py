@@ -34,9 +34,11 @@ rng = np.random.default_rng(11)
 ws = dr.trained_like_weights(MODELNET_DECODER, 5)
 mu = rng.standard_normal((40, 64)).astype(np.float32)
 variants = {'default': {}, 'l4_generic': {'env': {'A3D_L4_IMPL': 'generic'}}, 'tail_simt': {'env': {'A3D_TAIL_IMPL': 'simt'}},
-            'pair1': {'env': {'A3D_CONV_PAIR': '1'}}, 'pair2': {'env': {'A3D_CONV_PAIR': '2'}}, 'simt': {'impl': 'simt'},
+            'pair1': {'env': {'A3D_CONV_PAIR': '1'}}, 'pair2': {'env': {'A3D_CONV_PAIR': '2'}},
+            'pair3': {'env': {'A3D_CONV_PAIR': '3'}}, 'simt': {'impl': 'simt'},
             'bf16': {'operand_dtype': 'bf16'}}
 for name, kw in variants.items():
+    rng = np.random.default_rng(12)                   # every variant sees the same inputs (the test compares their digests)
     dec = make(MODELNET_DECODER, ws, **kw)
     sizes = (1, 5, 33) if name in ('simt', 'tail_simt') else (1, 5, 21, 33, 40, 72)
     for n in sizes:                                   # decoder(z): ragged n, several chunks of 32
