@@ -47,22 +47,6 @@ constexpr int kSmem = 1024 + 2 * kABytes + kWBytes + 2 * kExD + 16 * 8 + 16;
 
 __device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory"); }
 
-// the output non-linearity on a packed pair of logits (see SIG below)
-template <int SIG>
-__device__ __forceinline__ uint64_t squash(uint64_t o) {
-  if constexpr (SIG == 1) {
-    float a0, a1;
-    ptx::f2_unpack(ptx::f2_mul(o, ptx::f2_pack(0.5f, 0.5f)), a0, a1);
-    return ptx::f2_pack(ptx::tanh_approx(a0), ptx::tanh_approx(a1));
-  } else if constexpr (SIG >= 2) {
-    float a0, a1;
-    ptx::f2_unpack(o, a0, a1);
-    return ptx::f2_pack(__fdividef(1.f, 1.f + __expf(-a0)), __fdividef(1.f, 1.f + __expf(-a1)));
-  } else {
-    return o;
-  }
-}
-
 // SIG: 0 = linear output, 1 = sigmoid as 0.5 + 0.5 tanh(x / 2) (one MUFU per voxel; the counts-only path), 2 / 3 = sigmoid
 // as 1 / (1 + exp(-x)) (full relative accuracy near 0 and 1: used whenever probabilities (2) or the BCE loss (3) are
 // emitted; the loss code is compiled out of 2)
@@ -181,6 +165,7 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
     const int rm = ld >= 1 ? r - kDStep : r, rp = ld < kDLast ? r + kDStep : r;
     // lanes 0 / 31 sit on the grid border in h, their missing neighbour is the zero padding
     const uint64_t hmask = ptx::f2_pack(lane >= 1 ? 1.f : 0.f, lane <= 30 ? 1.f : 0.f);
+    const uint64_t half2 = ptx::f2_pack(0.5f, 0.5f);
     uint64_t* exq = reinterpret_cast<uint64_t*>(exD);   // exchange buffers as (ph = 0, ph = 1) pairs: [2][4][kRows]
     uint32_t it = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -212,85 +197,67 @@ tail_hcol_kernel(const __grid_constant__ CUtensorMap tmap_a4, const __grid_const
       uint64_t psum[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) psum[p] = 0ull;
-      // The K samples of the item.  Work that can only reach incomplete (dropped) outputs is compiled out per warp: w-slice
-      // 0 of a block completes no pw = 0 output and slice 3 no pw = 1 output (the partner slice lies in the neighbouring
-      // block); d line 0 completes no pd = 0 output and sends nothing to a line below, d line 3 no pd = 1 output and
-      // nothing upwards.  (slice, d line) are fixed per warp, so the loop is instantiated for the nine combinations and
-      // every warp runs straight-line code: the full-work warps are unchanged, the border warps issue 50-75 % of it.
-      // (A run-time-predicated version needed a second tcgen05.ld round trip per sample to stay under 96 registers and
-      // was slower: profiles/r02_notes.md section 12.)
-      auto samples = [&](auto pw0_c, auto pw1_c, auto pd0_c, auto pd1_c) {
-        constexpr bool PW0 = decltype(pw0_c)::value, PW1 = decltype(pw1_c)::value;
-        constexpr bool PD0 = decltype(pd0_c)::value, PD1 = decltype(pd1_c)::value;
-        for (int kp = 0; kp < K; ++kp, ++it) {
-          const int s = it & 1;
-          ptx::mbar_wait(&t_full[s], (it >> 1) & 1);
-          ptx::tc_fence_after();
-          const uint32_t tblk = tmem_base + lane_base + s * 256;
-          uint32_t ya[2][16];   // Za [pw][td][j]
-          uint32_t zn[2][16];   // [0]: Zm of slice m - 1 -> pw = 0;  [1]: Zp of slice m + 1 -> pw = 1   [td][j]
-          if constexpr (PW0) {
-            ptx::tmem_ld16(tblk + m * 64, ya[0]);
-            ptx::tmem_ld16(tblk + (m - 1) * 64 + 32, zn[0]);
-          }
-          if constexpr (PW1) {
-            ptx::tmem_ld16(tblk + m * 64 + 16, ya[1]);
-            ptx::tmem_ld16(tblk + (m + 1) * 64 + 48, zn[1]);
-          }
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   // accumulators are in registers: release the TMEM buffer
-          // ---- w axis (register pairs) and h axis (lanes are the 32 h positions):
-          //      out_h[ph=0] = Z[th=1] + Z_{h-1}[th=3];  out_h[ph=1] = Z[th=2] + Z_{h+1}[th=0]
-          uint64_t zh[4][2];   // [td][pw] as (ph = 0, ph = 1)
+      for (int kp = 0; kp < K; ++kp, ++it) {
+        const int s = it & 1;
+        ptx::mbar_wait(&t_full[s], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t tblk = tmem_base + lane_base + s * 256;
+        uint32_t ya[2][16];   // Za [pw][td][j]
+        uint32_t zn[2][16];   // [0]: Zm of slice m - 1 -> pw = 0;  [1]: Zp of slice m + 1 -> pw = 1   [td][j]
+        ptx::tmem_ld16(tblk + m * 64, ya[0]);
+        ptx::tmem_ld16(tblk + m * 64 + 16, ya[1]);
+        // slices outside the block: any in-range address (the values only reach outputs that are masked below)
+        ptx::tmem_ld16(tblk + (m > 0 ? m - 1 : 0) * 64 + 32, zn[0]);
+        ptx::tmem_ld16(tblk + (m < 3 ? m + 1 : 3) * 64 + 48, zn[1]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   // accumulators are in registers: release the TMEM buffer
+        // ---- w axis (register pairs) and h axis (lanes are the 32 h positions):
+        //      out_h[ph=0] = Z[th=1] + Z_{h-1}[th=3];  out_h[ph=1] = Z[th=2] + Z_{h+1}[th=0]
+        uint64_t zh[4][2];   // [td][pw] as (ph = 0, ph = 1)
 #pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            if ((pw == 0 && !PW0) || (pw == 1 && !PW1)) continue;
+        for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-            for (int td = 0; td < 4; ++td) {
-              // td 0 goes to the d - 1 line and td 1 into this row's pd = 0 outputs (both need ld >= 1); td 2 into its
-              // pd = 1 outputs and td 3 to the d + 1 line (both need ld <= 2)
-              if ((td < 2 && !PD0) || (td >= 2 && !PD1)) continue;
-              const uint32_t* y = &ya[pw][td * 4];
-              const uint32_t* n = &zn[pw][td * 4];
-              const uint64_t c = ptx::f2_add(ptx::f2_pack_bits(y[0], y[1]), ptx::f2_pack_bits(n[0], n[1]));   // th 1, 2
-              const uint64_t o = ptx::f2_add(ptx::f2_pack_bits(y[2], y[3]), ptx::f2_pack_bits(n[2], n[3]));   // th 3, 0
-              float o3, o0;
-              ptx::f2_unpack(o, o3, o0);
-              const float up = __shfl_up_sync(0xffffffffu, o3, 1);
-              const float dn = __shfl_down_sync(0xffffffffu, o0, 1);
-              zh[td][pw] = ptx::f2_fma(ptx::f2_pack(up, dn), hmask, c);
-            }
+          for (int td = 0; td < 4; ++td) {
+            const uint32_t* y = &ya[pw][td * 4];
+            const uint32_t* n = &zn[pw][td * 4];
+            const uint64_t c = ptx::f2_add(ptx::f2_pack_bits(y[0], y[1]), ptx::f2_pack_bits(n[0], n[1]));   // th 1, 2
+            const uint64_t o = ptx::f2_add(ptx::f2_pack_bits(y[2], y[3]), ptx::f2_pack_bits(n[2], n[3]));   // th 3, 0
+            float o3, o0;
+            ptx::f2_unpack(o, o3, o0);
+            const float up = __shfl_up_sync(0xffffffffu, o3, 1);
+            const float dn = __shfl_down_sync(0xffffffffu, o0, 1);
+            zh[td][pw] = ptx::f2_fma(ptx::f2_pack(up, dn), hmask, c);
           }
-          // ---- d axis through shared memory (double buffered across samples: one tile barrier per sample)
-          uint64_t* ex = exq + (it & 1) * (4 * kRows);
+        // ---- d axis through shared memory (double buffered across samples: one tile barrier per sample)
+        uint64_t* ex = exq + (it & 1) * (4 * kRows);
 #pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            if ((pw == 0 && !PW0) || (pw == 1 && !PW1)) continue;
-            if constexpr (PD1) ex[(0 * 2 + pw) * kRows + r] = zh[3][pw];
-            if constexpr (PD0) ex[(1 * 2 + pw) * kRows + r] = zh[0][pw];
-          }
-          tile_sync(m);
-#pragma unroll
-          for (int pw = 0; pw < 2; ++pw) {
-            if ((pw == 0 && !PW0) || (pw == 1 && !PW1)) continue;
-            if constexpr (PD0) psum[0 * 2 + pw] = ptx::f2_add(psum[0 * 2 + pw], squash<SIG>(ptx::f2_add(zh[1][pw], ex[(0 * 2 + pw) * kRows + rm])));
-            if constexpr (PD1) psum[1 * 2 + pw] = ptx::f2_add(psum[1 * 2 + pw], squash<SIG>(ptx::f2_add(zh[2][pw], ex[(1 * 2 + pw) * kRows + rp])));
-          }
+        for (int pw = 0; pw < 2; ++pw) {
+          ex[(0 * 2 + pw) * kRows + r] = zh[3][pw];
+          ex[(1 * 2 + pw) * kRows + r] = zh[0][pw];
         }
-      };
-      {
-        constexpr std::true_type T{};
-        constexpr std::false_type F{};
-        auto by_d = [&](auto pw0_c, auto pw1_c) {
-          if (ld == 0) samples(pw0_c, pw1_c, F, T);
-          else if (ld == kDLast) samples(pw0_c, pw1_c, T, F);
-          else samples(pw0_c, pw1_c, T, T);
-        };
-        if (m == 0) by_d(F, T);
-        else if (m == 3) by_d(T, F);
-        else by_d(T, T);
+        tile_sync(m);
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          uint64_t o0 = ptx::f2_add(zh[1][pw], ex[(0 * 2 + pw) * kRows + rm]);
+          uint64_t o1 = ptx::f2_add(zh[2][pw], ex[(1 * 2 + pw) * kRows + rp]);
+          if constexpr (SIG == 1) {
+            float a0, a1, b0, b1;
+            ptx::f2_unpack(ptx::f2_mul(o0, half2), a0, a1);
+            ptx::f2_unpack(ptx::f2_mul(o1, half2), b0, b1);
+            o0 = ptx::f2_pack(ptx::tanh_approx(a0), ptx::tanh_approx(a1));
+            o1 = ptx::f2_pack(ptx::tanh_approx(b0), ptx::tanh_approx(b1));
+          } else if constexpr (SIG >= 2) {
+            float a0, a1, b0, b1;
+            ptx::f2_unpack(o0, a0, a1);
+            ptx::f2_unpack(o1, b0, b1);
+            o0 = ptx::f2_pack(__fdividef(1.f, 1.f + __expf(-a0)), __fdividef(1.f, 1.f + __expf(-a1)));
+            o1 = ptx::f2_pack(__fdividef(1.f, 1.f + __expf(-b0)), __fdividef(1.f, 1.f + __expf(-b1)));
+          }
+          psum[0 * 2 + pw] = ptx::f2_add(psum[0 * 2 + pw], o0);
+          psum[1 * 2 + pw] = ptx::f2_add(psum[1 * 2 + pw], o1);
+        }
       }
       if constexpr (SIG == 1) {
         // counts-only path (no probabilities, no loss: the launcher picks SIG = 1 only then): branch-free bit masks over
