@@ -2,8 +2,8 @@
 // weight-stationary 2-CTA tcgen05 kernel that SWEEPS ALONG W and resolves the w taps inside a ring of TMEM accumulators.
 //
 // Why: in the round-1 kernel (h-sweep, removed; profiles/r01_l4_ws2cta_ncu_full.txt) the delta_w = -1 / +1 taps were
-// separate N = 64 MMAs over w-shifted views of the activation tile.  An N = 64 MMA reads 5 KB of shared-memory operands per 32 tensor clocks, more than the 128 B/clk
-// the port delivers: that kernel sat at 81 % tensor-active, port bound.  Here every MMA is M = 256 (CTA pair), N = 256:
+// separate N = 64 MMAs over w-shifted views of the activation tile.  An N = 64 MMA reads 5 KB of shared-memory operands
+// per 32 tensor clocks, more than the 128 B/clk the port delivers: that kernel sat at 81 % tensor-active, port bound.  Here every MMA is M = 256 (CTA pair), N = 256:
 // 8 KB of operands per 128 tensor clocks per CTA = half the port.
 //
 // Formulation.  Output voxel w_o = 2 j_o + pw receives input column j = j_o + dw through tap tw = pw + 1 - 2 dw, so
@@ -23,9 +23,11 @@
 //     MMAs accumulate and no MMA ever has to mix fresh and live columns.
 //   * Items (decode-block pair, d) are 16 steps; consecutive items of a cluster start alternately in phase A and C, so
 //     the first window of an item never touches a slot the previous item's last drain still owns.
-// Otherwise: clusters own one (pd, ph) output-parity class for the whole launch (128 KB
-// of weights per CTA resident in shared memory), activation tiles stream through a 4-stage TMA ring, the leader CTA's
-// MMA warp drives both SMs, 8 epilogue warps per CTA (folded BN + activation + 16-bit pack + staged 64-byte stores).
+// Otherwise: clusters own one (pd, ph) output-parity class for the whole launch (128 KB of weights per CTA resident in
+// shared memory, loaded before the programmatic-dependent-launch wait), activation tiles stream through a 4-stage TMA
+// ring, the leader CTA's MMA warp drives both SMs, 16 epilogue warps per CTA (a drained slot is handed back first, then
+// folded BN + activation + 16-bit pack + staged 32-byte-sector stores), item schedule in l4_sched.h, soft pacing of the
+// clusters through per-cluster progress counters (L2 reuse of the activation planes).
 #include <cstdlib>
 
 #include "epilogue.cuh"
@@ -121,7 +123,7 @@ convt_l4_sw_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint64_t* a_full = bars;                    // [A_STAGES]  leader: 1 arrival + both CTAs' bytes
   uint64_t* a_empty = a_full + A_STAGES;      // [A_STAGES]  per CTA, multicast commit
   uint64_t* s_full = a_empty + A_STAGES;      // [NSLOT]     per CTA, multicast commit: slot closed
-  uint64_t* s_empty = s_full + NSLOT;         // [NSLOT]     leader: 2 x 8 epilogue warps: slot drained and re-zeroed
+  uint64_t* s_empty = s_full + NSLOT;         // [NSLOT]     leader: 2 x 16 epilogue warps: slot drained and re-zeroed
   uint64_t* w_full = s_empty + NSLOT;         // leader: weights of both CTAs landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);   // 17 barriers + 8 bytes: 16-byte aligned for the float4 reads

@@ -18,14 +18,16 @@
 // decode blocks as ONE tcgen05 cta_group::2 MMA of M = 256.  They share every weight tile: each CTA loads and holds
 // only its N-half (contiguous row ranges of the repacked weights), which halves the TMA weight writes and the
 // B-operand reads -- these layers are bound by shared-memory bandwidth (MMA operand reads + TMA writes), not by the
-// tensor pipe.  PAIR = 1 keeps the single-CTA path (small calls, A3D_CONV_PAIR=1, and the 128->64 layer with A3D_L4_IMPL=generic).
+// tensor pipe.  PAIR = 1 keeps the single-CTA path (A3D_CONV_PAIR=1, and the 128->64 layer with A3D_L4_IMPL=generic);
+// HP pairs two input rows of ONE decode block instead (small calls); the launcher picks the variant per call size.
 //
 // Roles (384 threads): warps 0..7 = epilogue, warp 8 = TMEM allocator, warp 10 = TMA producer, warp 11 = MMA issuer
 // (converged warp; only tcgen05.mma / commit are predicated on an elected lane, so descriptors stay in uniform
 // registers).  fp32 accumulators are multi-buffered in TMEM (512 columns) so the epilogue of unit i overlaps the main
 // loop of unit i + 1.  Epilogue: tcgen05.ld -> scale/shift -> activation -> 16-bit -> XOR-swizzled 128-byte staging
-// rows in shared memory -> every warp-level store writes four complete 128-byte lines.  Persistent CTAs, static
-// round-robin unit schedule with the parity class of a CTA (pair) fixed.
+// rows in shared memory -> every warp-level store writes four complete 128-byte lines.  Persistent CTAs; static unit
+// schedule in walk.h (regular workers keep their parity class and rotate through the positions, helper workers use the
+// SMs a multiple of the class count leaves over); programmatic dependent launch (the prologue overlaps the previous layer).
 #include <cstdlib>
 
 #include "epilogue.cuh"
