@@ -4,13 +4,14 @@ A3D_LIB=<lib B> and prints value, stage times and clock of every run.
 Usage: python tests/tools/ab_libs.py liba3d_prev.so liba3d.so [rounds]"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-libs = sys.argv[1:3]
+libs = sys.argv[1:3]           # a library file name, or ENV=VALUE[,ENV=VALUE] to compare settings of the default library
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 acc = {l: [] for l in libs}
 for i in range(rounds):
     for l in libs:
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--no-aux', '--no-cpu-baseline'], capture_output=True, text=True,
-                           env=dict(os.environ, A3D_LIB=l), cwd=ROOT)
+                           env=dict(os.environ, **(dict(kv.split('=', 1) for kv in l.split(',') if kv) if ('=' in l or l == '-') else
+                                                   {'A3D_LIB': l})), cwd=ROOT)
         d = json.loads(r.stdout.strip().splitlines()[-1])
         st = {k: round(v, 3) for k, v in d['roofline']['stage_ms'].items()}
         acc[l].append(d['value'])
