@@ -558,10 +558,13 @@ def _main(args, saved_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
+    wall = [0.0, 0.0]      # wall-clock bounds of the last timed region (for the clock sampler)
+
     def timed_steps(n_steps, seed0=0, keep=None):
         """n_steps steps, counts accumulated on the device, ONE all-reduce at the end; CUDA events, max over ranks."""
         acc = torch.zeros(3, dtype=torch.int64, device=dev)
         barrier()
+        wall[0] = time.time()          # after the barrier: the first one of a run creates the NCCL communicator (idle GPU)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n_steps):
@@ -569,6 +572,8 @@ def _main(args, saved_stdout):
         if dist is not None:
             dist.all_reduce(acc)       # the path's only collective: [TP, FP, FN] int64 over NVLink, once per run
         e1.record()
+        torch.cuda.synchronize()
+        wall[1] = time.time()
         barrier()
         ms = e0.elapsed_time(e1)
         if dist is not None:
@@ -590,9 +595,8 @@ def _main(args, saved_stdout):
         step(i, warm)
     l0 = dec.launch_count
     last_counts = []
-    t_wall0 = time.time()
     ms, total = timed_steps(args.steps, keep=last_counts)
-    t_wall1 = time.time()
+    t_wall0, t_wall1 = wall
     launches = dec.launch_count - l0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     obj_per_step = B_PER_RATE * len(RATES) * world
