@@ -77,21 +77,57 @@ def _crc32c_table():
 _CRC_TABLE = _crc32c_table()
 
 
+def _crc_bytes(data, reg: int) -> int:
+    """Per-byte table update of the raw CRC register (no init / final xor)."""
+    for b in data:
+        reg = _CRC_TABLE[(reg ^ b) & 0xFF] ^ (reg >> 8)
+    return reg
+
+
+def _crc32c_numpy(data: bytes, crc: int) -> int:
+    """CRC-32C of a large buffer without the native library: the buffer is cut into N equal chunks whose raw registers
+    (start value 0) are advanced in lock-step by vectorised table look-ups -- one numpy step per byte POSITION, not per
+    byte -- and then folded in order through the linear map 'append L zero bytes' (the CRC register update is linear
+    over GF(2) in (register, data)).  ~0.5 s for 80 MB instead of minutes for the per-byte loop."""
+    n = len(data)
+    lanes = 1 << 14
+    L = n // lanes
+    if L < 64:
+        return _crc_bytes(data, crc ^ 0xFFFFFFFF) ^ 0xFFFFFFFF
+    table = np.asarray(_CRC_TABLE, dtype=np.uint32)
+    body = np.frombuffer(data, dtype=np.uint8, count=lanes * L).reshape(lanes, L)
+    reg = np.zeros(lanes, dtype=np.uint32)
+    for j in range(L):
+        reg = table[(reg ^ body[:, j]) & 0xFF] ^ (reg >> 8)
+    # A_L: the register after L zero bytes, as four 256-entry tables (one per register byte); built from the 32 basis vectors
+    basis = np.array([1 << i for i in range(32)], dtype=np.uint32)
+    for _ in range(L):
+        basis = table[basis & 0xFF] ^ (basis >> 8)
+    shift = np.zeros((4, 256), dtype=np.uint32)
+    for k in range(4):
+        for bit in range(8):
+            sel = (np.arange(256) >> bit) & 1
+            shift[k] ^= np.where(sel == 1, basis[8 * k + bit], 0).astype(np.uint32)
+    sh = [[int(v) for v in shift[k]] for k in range(4)]
+    acc = crc ^ 0xFFFFFFFF
+    for r in reg.tolist():
+        acc = sh[0][acc & 0xFF] ^ sh[1][(acc >> 8) & 0xFF] ^ sh[2][(acc >> 16) & 0xFF] ^ sh[3][acc >> 24] ^ r
+    return _crc_bytes(data[lanes * L:], acc) ^ 0xFFFFFFFF
+
+
 def crc32c(data: bytes, crc: int = 0) -> int:
-    """CRC-32C (Castagnoli).  Large buffers go through liba3d's slice-by-8 host routine (a3d_crc32c); the pure-Python
-    loop below is the same polynomial and serves small index blocks or a missing library (this is file I/O, not the
-    compute path)."""
+    """CRC-32C (Castagnoli).  Large buffers go through liba3d's slice-by-8 host routine (a3d_crc32c); without the library
+    (a host that only converts checkpoints) a chunk-parallel numpy evaluation of the same polynomial takes over; small
+    index blocks use the per-byte table loop (this is file I/O, not the compute path)."""
     if len(data) >= 4096:
         try:
             from . import _capi
             buf = bytes(data)
             return int(_capi.lib().a3d_crc32c(buf, len(buf), crc))
         except (RuntimeError, OSError, AttributeError):
-            pass
-    c = crc ^ 0xFFFFFFFF
-    for b in data:
-        c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+            if len(data) >= (1 << 20):
+                return _crc32c_numpy(bytes(data), crc)
+    return _crc_bytes(data, crc ^ 0xFFFFFFFF) ^ 0xFFFFFFFF
 
 
 def _mask_crc(c: int) -> int:

@@ -19,6 +19,24 @@ def test_crc32c_and_varint_known_answers():
     assert tc._put_varint(300) == b'\xac\x02' and tc._varint(b'\xac\x02', 0) == (300, 2)
 
 
+def test_crc32c_numpy_fallback_matches_the_byte_loop_and_the_native_routine():
+    """Without liba3d (a host that only converts checkpoints) large tensors are checksummed by a chunk-parallel numpy
+    evaluation; it must agree with the per-byte table loop, with the native slice-by-8 routine and with chained start
+    values, for lengths around the chunking boundaries."""
+    rng = np.random.default_rng(5)
+    assert tc._crc32c_numpy(b'123456789', 0) == 0xE3069283          # short input: falls through to the byte loop
+    for n in ((1 << 20), (1 << 20) + 1, (1 << 20) + 16383, 3_000_017):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        want = tc._crc_bytes(d, 0xFFFFFFFF) ^ 0xFFFFFFFF if n < 1_200_000 else None
+        got = tc._crc32c_numpy(d, 0)
+        if want is not None:
+            assert got == want
+        assert got == tc.crc32c(d)                                  # native routine when the library is built
+        mid = n // 3
+        assert tc._crc32c_numpy(d[mid:], tc._crc32c_numpy(d[:mid], 0)) == got or mid < (1 << 20)
+        assert tc._crc32c_numpy(d[mid:], tc.crc32c(d[:mid])) == got
+
+
 def test_snappy_decoder_on_hand_built_stream():
     # literal "abcd", copy(offset 4, len 8) -> "abcdabcdabcd", literal "Z"
     stream = tc._put_varint(13) + bytes([(4 - 1) << 2]) + b'abcd' + bytes([((8 - 4) << 2) | 1, 4]) + bytes([0]) + b'Z'
