@@ -432,24 +432,12 @@ size_t convt_tc_smem_bytes(int cin, int cout, int win) {
 // single-CTA kernel saves scheduling rounds.  Cost = units of the busiest worker x relative unit time: 1 for the decode
 // pairing, 1 + 1 / (2 W) for the h pairing (its zero rows), `single_cost` for the single-CTA kernel (measured: it
 // streams every weight tile to every SM and is bound by the L2 -> SM fabric on the 512->256 layer).
-enum { kVarPair = 0, kVarHp = 1, kVarSingle = 2 };
+using conv_variant::kVarPair;
+using conv_variant::kVarHp;
+using conv_variant::kVarSingle;
 template <class C2>
 int pick_variant(int64_t n, int num_sms, float single_cost) {
-  const int nb = (int)((n + C2::NT - 1) / C2::NT);
-  auto rounds = [](int npar, int n_pos, int workers) {      // units of the busiest worker
-    if (workers > n_pos * npar) workers = n_pos * npar;
-    const Walk w = make_walk(npar, n_pos, workers);
-    const int r = w.reg / npar;
-    const int reg_rounds = (w.pos_reg + r - 1) / r;
-    const int help_rounds = w.helpers > 0 ? (npar / w.helpers) * (n_pos - w.pos_reg) : 0;
-    return reg_rounds > help_rounds ? reg_rounds : help_rounds;
-  };
-  constexpr int WW = C2::WIN * C2::WIN;
-  const float c_pair = (float)rounds(C2::NPAR, ((nb + 1) / 2) * WW, num_sms / 2);
-  const float c_hp = rounds(C2::NPAR, nb * WW / 2, num_sms / 2) * (1.f + 0.5f / C2::WIN);
-  const float c_single = rounds(C2::NPAR, nb * WW, num_sms) * single_cost;
-  if (c_pair <= c_hp && c_pair <= c_single) return kVarPair;
-  return c_hp <= c_single ? kVarHp : kVarSingle;
+  return conv_variant::pick(n, C2::NT, C2::WIN, C2::NPAR, num_sms, single_cost);
 }
 
 int launch_convt_s2_tc(const ConvLayer& L, void* out, int64_t n, int64_t n_alloc, int fmt, int act, int num_sms,

@@ -60,4 +60,29 @@ A3D_HD inline Walk make_walk(int npar, int n_pos, int workers) {
 }
 
 
+// Variant choice of the row-unit kernel per call size (host only).  Cost = units of the busiest worker x relative unit
+// time: 1 for the decode pairing, 1 + 1 / (2 W) for the h pairing (its zero rows), `single_cost` for the single-CTA kernel
+// (measured: it streams every weight tile to every SM and is bound by the L2 -> SM fabric on the 512->256 layer).
+namespace conv_variant {
+enum { kVarPair = 0, kVarHp = 1, kVarSingle = 2 };
+inline int busiest(int npar, int n_pos, int workers) {      // units of the busiest worker
+  if (workers > n_pos * npar) workers = n_pos * npar;
+  const Walk w = make_walk(npar, n_pos, workers);
+  const int r = w.reg / npar;
+  const int reg_rounds = (w.pos_reg + r - 1) / r;
+  const int help_rounds = w.helpers > 0 ? (npar / w.helpers) * (n_pos - w.pos_reg) : 0;
+  return reg_rounds > help_rounds ? reg_rounds : help_rounds;
+}
+// n decodes, nt decodes per block, win = input grid, npar parity classes per position
+inline int pick(long long n, int nt, int win, int npar, int num_sms, float single_cost) {
+  const int nb = (int)((n + nt - 1) / nt);
+  const int ww = win * win;
+  const float c_pair = (float)busiest(npar, ((nb + 1) / 2) * ww, num_sms / 2);
+  const float c_hp = busiest(npar, nb * ww / 2, num_sms / 2) * (1.f + 0.5f / win);
+  const float c_single = busiest(npar, nb * ww, num_sms) * single_cost;
+  if (c_pair <= c_hp && c_pair <= c_single) return kVarPair;
+  return c_hp <= c_single ? kVarHp : kVarSingle;
+}
+}  // namespace conv_variant
+
 }  // namespace a3d

@@ -137,3 +137,46 @@ def test_l4_item_schedule_covers_every_item_exactly_once(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.startswith('OK'), r.stdout
+
+
+VARIANT_PROGRAM = textwrap.dedent(r'''
+    #include <cstdio>
+    #include "walk.h"
+    using namespace a3d::conv_variant;
+    int main() {
+      // (layer geometry: decodes per block, input grid, parity classes, single-CTA cost) x call size -> expected variant
+      struct Case { int nt, win, npar; float single; long long n; int want; };
+      const Case cases[] = {
+        {32, 4, 8, 1.6f, 32, kVarHp},      // 512->256 layer, ONE decode block: two rows of it per pair
+        {32, 4, 8, 1.6f, 64, kVarPair},    // two blocks: the decode pairing is full
+        {32, 4, 8, 1.6f, 72, kVarHp},      // three blocks (getEval batch 72)
+        {32, 4, 8, 1.6f, 4096, kVarPair},
+        {32, 4, 8, 1.6f, 8192, kVarPair},
+        {16, 8, 4, 1.15f, 32, kVarPair},   // 256->128 layer
+        {16, 8, 4, 1.15f, 72, kVarHp},     // five blocks: the decode pairing would run a sixth, empty one
+        {16, 8, 4, 1.15f, 4096, kVarPair},
+      };
+      for (const Case& c : cases) {
+        const int got = pick(c.n, c.nt, c.win, c.npar, 148, c.single);
+        if (got != c.want) { printf("n %lld (nt %d): variant %d, expected %d\n", c.n, c.nt, got, c.want); return 1; }
+      }
+      // large even block counts always take the decode pairing (the h pairing pays for its zero rows, the single-CTA kernel
+      // for its weight traffic)
+      for (long long n = 1024; n <= 16384; n += 1024)
+        if (pick(n, 32, 4, 8, 148, 1.6f) != kVarPair || pick(n, 16, 8, 4, 148, 1.15f) != kVarPair) { printf("large n %lld\n", n); return 1; }
+      printf("OK\n");
+      return 0;
+    }
+''')
+
+
+def test_variant_choice_of_the_row_unit_kernel(tmp_path):
+    """csrc/walk.h conv_variant::pick: the per-call choice between decode pairing, h pairing and the single-CTA kernel is
+    pinned for the reference's call shapes (32 / 72 latents) and for the bench's chunks."""
+    src = tmp_path / 'variant_test.cpp'
+    src.write_text(VARIANT_PROGRAM)
+    exe = tmp_path / 'variant_test'
+    r = subprocess.run(['g++', '-O1', '-std=c++17', '-I', CSRC, str(src), '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == 'OK', r.stdout
